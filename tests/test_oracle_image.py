@@ -1,0 +1,135 @@
+"""Pins oracle/image_oracle.py (samplers, operators, parameter table) against the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import image_oracle as io_
+from oracle import ref_loader
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden.npz"))
+
+
+def _den():
+    den = io_.DnCNN(depth=4, nf=8)
+    den.load_state_dict({k[4:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("den.")})
+    return den.eval()
+
+
+def test_inpainting_operator_golden():
+    im = torch.from_numpy(G["im"])
+    inp = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    assert np.array_equal(inp["mask"].numpy(), G["inp.mask"])
+    assert np.array_equal(inp["y"].numpy(), G["inp.y"])
+    assert np.array_equal(inp["init"].numpy(), G["inp.init"])
+
+
+def test_deblurring_operator_golden():
+    im = torch.from_numpy(G["im"])
+    deb = io_.make_deblurring(im, l=2, blur_type="gaussian", si=1.0, sigma=1.0, seed_ip=0)
+    assert np.array_equal(deb["h"], G["deb.h"])
+    assert np.allclose(deb["A"](im).numpy(), G["deb.Ax"], atol=1e-7)
+    assert np.allclose(deb["y"].numpy(), G["deb.y"], atol=1e-7)
+    assert np.allclose(deb["data_grad"](im).numpy(), G["deb.grad_at_im"], rtol=1e-5, atol=1e-2)
+
+
+def test_psgla_golden_replay_and_seeded():
+    im = torch.from_numpy(G["im"])
+    inp = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    alpha, lambd, s, delta, n_iter, n_inter, n_mm = G["psgla.params"]
+    kw = dict(init=inp["init"], data_grad=inp["data_grad"], denoiser=_den(), alpha=torch.tensor(float(alpha), dtype=torch.float32),
+              lambd=torch.tensor(float(lambd)), sig_float=float(s), delta=float(delta), n_iter=int(n_iter),
+              n_inter=int(n_inter), n_inter_mmse=int(n_mm))
+    for extra in (dict(seed=0), dict(noise=torch.from_numpy(G["psgla.noise"]))):
+        Xl, Xm, Xm2 = io_.psgla(**kw, **extra)
+        assert len(Xl) == 8 and len(Xm) == 4  # thinning / window bookkeeping (restoration_algorithms.py:241,256-271)
+        assert np.allclose(torch.stack(Xl).numpy(), G["psgla.X"], atol=1e-6)
+        assert np.allclose(torch.stack(Xm).numpy(), G["psgla.M"], atol=1e-6)
+        assert np.allclose(torch.stack(Xm2).numpy(), G["psgla.M2"], atol=1e-6)
+
+
+def test_pnpula_golden_replay():
+    im = torch.from_numpy(G["im"])
+    deb = io_.make_deblurring(im, l=2, blur_type="gaussian", si=1.0, sigma=1.0, seed_ip=0)
+    delta, lam, alpha, s1, s2, n_iter, n_inter, n_mm, _ = G["ula.params"]
+    pg = io_.make_prior_grad(_den(), float(alpha), float(s1), float(s2))
+    Xl, Xm, Xm2 = io_.pnpula(init=deb["init"], data_grad=deb["data_grad"], prior_grad=pg,
+                             delta=torch.tensor(float(delta), dtype=torch.float32), lambd=torch.tensor(float(lam), dtype=torch.float32),
+                             n_iter=int(n_iter), n_inter=int(n_inter), n_inter_mmse=int(n_mm), noise=torch.from_numpy(G["ula.noise"]))
+    assert len(Xl) == 8 and len(Xm) == 4
+    assert np.allclose(torch.stack(Xl).numpy(), G["ula.X"], atol=2e-6)
+    assert np.allclose(torch.stack(Xm).numpy(), G["ula.M"], atol=2e-6)
+    assert np.allclose(torch.stack(Xm2).numpy(), G["ula.M2"], atol=2e-6)
+
+
+def test_resolve_params_table():
+    p = io_.resolve_params("psgla")  # sampling_images.py:170-198 defaults
+    assert p["s"] == 2.0 / 255 and p["lambd"] == 5.0 and p["delta"] == (2.0 / 255) ** 2 and p["n_inter"] == 10
+    assert abs((p["delta"] / p["lambd"]) / p["sigma2"] - 0.8) < 1e-12
+    q = io_.resolve_params("pnp_ula")  # double /255 quirk, N=100000, n_inter from the parsed N
+    assert q["N"] == 100000 and q["n_inter"] == 10
+    assert abs(q["s1"] - 2.0 / 255 / 255) < 1e-18
+    assert abs(q["lambd"] - 4.73e-10) / 4.73e-10 < 2e-3 and abs(q["delta"] - 1.05e-10) / 1.05e-10 < 5e-3
+    q5 = io_.resolve_params("pnp_ula", s=5.0)
+    assert abs(q5["lambd"] - 3.77e-6) / 3.77e-6 < 2e-3 and abs(q5["delta"] - 1.00e-6) / 1.00e-6 < 5e-3
+
+
+def test_window_count_rule():
+    # a window closes after n_inter_mmse+1 iterations => floor(N/(n_inter_mmse+1)) entries
+    x0 = torch.zeros(1, 3, 4, 4)
+    Xl, Xm, _ = io_.psgla(x0, lambda x: -x, _IdDen(), torch.tensor(1.0), torch.tensor(1.0), 0.01, 1e-4, n_iter=100,
+                          n_inter=10, n_inter_mmse=10, seed=0)
+    assert len(Xl) == 10 and len(Xm) == 100 // 11
+
+
+class _IdDen:
+    def forward(self, x, s):
+        return x
+
+
+def test_psnr_ssim_sanity():
+    rng = np.random.default_rng(0)
+    a = rng.uniform(size=(32, 32, 3))
+    assert io_.ssim(a, a) == pytest.approx(1.0)
+    b = np.clip(a + 0.1, 0, 2)
+    assert io_.psnr(a, b) == pytest.approx(20.0, abs=1e-6)
+
+
+def test_dncnn_weights_deterministic_and_contractive():
+    sd1 = io_.make_dncnn_weights(seed=0, n_power_iter=8, spatial=16)
+    sd2 = io_.make_dncnn_weights(seed=0, n_power_iter=8, spatial=16)
+    assert all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    assert sd1["in_conv.weight"].shape == (64, 3, 3, 3) and sd1["conv_list.17.weight"].shape == (64, 64, 3, 3)
+    assert sum(v.numel() for v in sd1.values()) == 668227
+    net = io_.DnCNN()
+    net.load_state_dict(sd1)
+    x1, x2 = torch.rand(1, 3, 24, 24), torch.rand(1, 3, 24, 24)
+    with torch.no_grad():
+        r1, r2 = net(x1) - x1, net(x2) - x2
+    assert (r1 - r2).norm() <= 1.0 * (x1 - x2).norm()
+
+
+@pytest.mark.reference
+def test_live_reference_bit_identical():
+    ra = ref_loader.load_restoration_algorithms()
+    im = torch.from_numpy(G["im"])
+    den = _den()
+    inp = io_.make_inpainting(im)
+    kw = dict(init=inp["init"], data_grad=inp["data_grad"], denoiser=den, alpha=torch.tensor(1.0), lambd=torch.tensor(5.0),
+              sig_float=2 / 255, delta=(2 / 255) ** 2, seed=11, device="cpu", n_iter=30, n_inter=4, n_inter_mmse=5)
+    a = ra.psgla(**kw)
+    b = io_.psgla(**kw)
+    for la, lb in zip(a, b):
+        assert len(la) == len(lb)
+        assert all(torch.equal(x, y) for x, y in zip(la, lb))
+    deb = io_.make_deblurring(im, l=4, blur_type="uniform")
+    p = io_.resolve_params("pnp_ula", s=5.0)
+    pg = io_.make_prior_grad(den, 1.0, p["s1"], p["s2"])
+    kw = dict(init=deb["init"], data_grad=deb["data_grad"], prior_grad=pg, delta=torch.tensor(p["delta"], dtype=torch.float32),
+              lambd=torch.tensor(p["lambd"], dtype=torch.float32), seed=2, device="cpu", n_iter=30, n_inter=4, n_inter_mmse=5)
+    a = ra.pnpula(**kw)
+    b = io_.pnpula(**kw)
+    for la, lb in zip(a, b):
+        assert len(la) == len(lb)
+        assert all(torch.equal(x, y) for x, y in zip(la, lb))
