@@ -1,0 +1,189 @@
+/*
+ * psgla_b200.h -- C ABI of the B200-native PSGLA / PnP-ULA hot path (libpsgla_b200.so).
+ *
+ * The reference (Marien-RENAUD/PSGLA-for-posterior-sampling) has no FFI layer: its boundary is the
+ * Python call signatures of the samplers plus four opaque callables.  Each entry point below
+ * names the reference lines whose arithmetic it replaces.  Python binds these with ctypes
+ * (psgla-for-posterior-sampling_b200/_lib.py); INTEGRATION.md shows the stub a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  "dev" pointers are CUDA device pointers owned by the caller
+ *     (torch allocates inputs, outputs and workspace); the library never frees caller memory.
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), asynchronous, re-entrant.
+ *   - return value: 0 = ok; >0 = cudaError_t; <0 = PSGLA_E_* below.  psgla_last_error() gives a thread-local message.
+ *   - image tensors are fp32 NCHW [B][3][H][W] ("chains" = B); denoiser activations are bf16 NHWC, library-internal.
+ *   - noise: in-kernel Philox4x32-10 keyed by (seed; subsequence = global chain id; counter = step / element), or,
+ *     when a replay pointer is given, the caller's N(0,1) draws (the reference's np.random.randn / torch.randn).
+ */
+#ifndef PSGLA_B200_H
+#define PSGLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PSGLA_ABI_VERSION 1
+
+enum {
+  PSGLA_OK = 0,
+  PSGLA_E_BADARG = -1,      /* null pointer, size out of range, unsupported option */
+  PSGLA_E_UNSUPPORTED = -2, /* valid request this build cannot serve (e.g. r > PSGLA_GMM_MAX_COMPONENTS) */
+  PSGLA_E_NODEVICE = -3,    /* no sm_100 device / driver entry point missing */
+  PSGLA_E_WORKSPACE = -4    /* workspace too small */
+};
+
+const char* psgla_last_error(void);
+int psgla_abi_version(void);
+/* compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int psgla_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2D Gaussian-mixture posterior sampling: replaces the Python loops of sampling_2D.py:21-45 (PnP_ULA) and
+ * sampling_2D.py:48-72 (SnoPnP_ULA = PSGLA) together with the closed-form MMSE denoiser utils_2D.py:209-233 and the
+ * data-fidelity score sampling_2D.py:30-31.  One thread owns one chain for all n_steps; nothing but the final state
+ * (and optional thinned trajectory) touches HBM.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define PSGLA_GMM_MAX_COMPONENTS 16
+#define PSGLA_ALG_PSGLA 0   /* x+ = D(x + (delta/alpha) score(x) + sqrt(2 delta) z, delta)            sampling_2D.py:63 */
+#define PSGLA_ALG_PNPULA 1  /* x+ = x + delta score(x) + alpha delta/eps (D(x,eps)-x) + sqrt(2 delta) z  sampling_2D.py:36 */
+
+typedef struct psgla_gmm2d_problem {
+  int32_t alg;          /* PSGLA_ALG_* */
+  int32_t n_components; /* r, 1..PSGLA_GMM_MAX_COMPONENTS */
+  double delta;         /* step size */
+  double alpha;         /* regularisation / relaxation parameter */
+  double epsilon;       /* denoiser level for PnP-ULA (PSGLA uses delta, sampling_2D.py:63) */
+  double sigma;         /* score = A^T (y - A x) / sigma^2                      sampling_2D.py:31 */
+  double A[4];          /* row-major 2x2 */
+  double y[2];
+  double mu[PSGLA_GMM_MAX_COMPONENTS][2];
+  double Sigma[PSGLA_GMM_MAX_COMPONENTS][4]; /* row-major 2x2, SPD */
+  double pi[PSGLA_GMM_MAX_COMPONENTS];
+} psgla_gmm2d_problem;
+
+/* Runs n_steps Langevin steps on n_chains chains.
+ *   precision   0: fp32 state and arithmetic (throughput path); 1: fp64 (parity path vs the float64 reference).
+ *   x_dev       [n_chains][2] of float/double: in = current state (x_0), out = state after n_steps.
+ *   chain_id0   global id of x_dev[0] (Philox subsequence), so results do not depend on how chains are sharded.
+ *   step0       global index of the first step (Philox counter), so a run may be split into segments.
+ *   noise_dev   NULL (Philox) or [n_steps][n_chains][2] standard normals of the same precision (replay).
+ *   traj_dev    NULL or [n_steps/thin][n_chains][2]: state after every global step t with (t+1) % thin == 0.
+ */
+int psgla_gmm2d_run(const psgla_gmm2d_problem* problem, int precision, void* x_dev, int64_t n_chains,
+                    int64_t chain_id0, int64_t n_steps, int64_t step0, uint64_t seed, const void* noise_dev,
+                    void* traj_dev, int64_t thin, void* stream);
+
+/* The denoiser alone on n points (utils_2D.py:219-232, log-sum-exp form): out = D(x, epsilon). */
+int psgla_gmm2d_denoise(const psgla_gmm2d_problem* problem, double epsilon, int precision, const void* x_dev,
+                        void* out_dev, int64_t n, void* stream);
+
+/* Standard normals from the library's Philox stream, exactly the draws psgla_gmm2d_run consumes for
+ * (chain_id0.., step0..): out_dev [n_steps][n_chains][2] fp32.  Test / replay aid. */
+int psgla_gmm2d_noise(float* out_dev, int64_t n_chains, int64_t chain_id0, int64_t n_steps, int64_t step0,
+                      uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Image inverse problems.  One "iteration" of psgla (restoration_algorithms.py:232-238) or pnpula (:104-115) on a
+ * batch of B independent chains of shape [3][H][W] is
+ *     pre   : data-fidelity gradient (+ projection term for PnP-ULA) + noise  -> base (fp32) and the denoiser input
+ *     dncnn : 20 conv3x3 layers (tcgen05 implicit GEMM, bf16 in / fp32 accumulate)
+ *     post  : fused into the last conv's epilogue: X+ = base + gain * (out_conv(h) + bias), thinning, E[X], E[X^2]
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct psgla_img_shape {
+  int32_t B, C, H, W; /* chains, channels (3), rows, cols */
+} psgla_img_shape;
+
+/* Inpainting "pre" (sampling_images.py:295 data_grad; restoration_algorithms.py:236 / :110-115):
+ *   PSGLA  : base = X + gain_data * (-mask (X - y)) + noise_scale * Z        (gain_data = (delta/lambd)/sigma^2)
+ *            den_in = bf16(base)
+ *   PnP-ULA: base = X + delta * (-(X - clamp(X,cmin,cmax))/lambd) + gain_data * (-mask (X - y)) + noise_scale * Z
+ *            den_in = bf16(X)                                              (gain_data = delta/sigma^2)
+ * mask_dev, y_dev: [1 or B][C][H][W] fp32 (mask_B / y_B say which; 1 = shared by all chains).
+ * noise_dev: NULL (Philox: subsequence = chain_id0 + b, counter = (iteration, element)) or [B][C][H][W] fp32.
+ * den_in_dev: bf16 NHWC [B][H][W][16] (channels 3..15 zero) -- the padded input of the first conv layer. */
+typedef struct psgla_pre_params {
+  int32_t alg;        /* PSGLA_ALG_* */
+  float gain_data;    /* multiplies -mask (X - y) resp. -A^T(A X - y) */
+  float noise_scale;  /* sqrt(2) s  resp.  sqrt(2 delta) */
+  float proj_gain;    /* PnP-ULA: delta / lambd; PSGLA: 0 */
+  float c_min, c_max; /* PnP-ULA projection box, restoration_algorithms.py:38 defaults -1, 2 */
+  uint64_t seed;
+  int64_t chain_id0;
+  int64_t iteration;
+} psgla_pre_params;
+
+int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape shape, const float* x_dev, const float* mask_dev,
+                          int mask_B, const float* y_dev, int y_B, const float* noise_dev, float* base_dev,
+                          void* den_in_dev, void* stream);
+
+/* Deblurring "pre" (sampling_images.py:329-338): data_grad = -A^T(A x - y)/sigma^2 with A = AT = separable circular
+ * blur with taps h1d[2l+1] (float, host pointer; symmetric by construction, sampling_images.py:306-314).
+ * The blur is a shared-memory staged stencil: tile + 2l halo, wrap-around indexing. */
+int psgla_img_pre_deblur(const psgla_pre_params* p, psgla_img_shape shape, const float* x_dev, const float* h1d_host,
+                         int l, const float* y_dev, int y_B, const float* noise_dev, float* base_dev,
+                         void* den_in_dev, void* stream);
+/* y = A x alone (builds the observation, sampling_images.py:335). */
+int psgla_img_blur(psgla_img_shape shape, const float* x_dev, const float* h1d_host, int l, float* out_dev,
+                   void* stream);
+
+/* Fills out_dev [B][C][H][W] with the N(0,1) draws the "pre" kernels consume for (seed, chain_id0, iteration). */
+int psgla_img_noise(psgla_img_shape shape, uint64_t seed, int64_t chain_id0, int64_t iteration, float* out_dev,
+                    void* stream);
+
+/* DnCNN (deepinv.models.DnCNN as constructed at sampling_images.py:130; called restoration_algorithms.py:238 and
+ * sampling_images.py:156): depth conv3x3 layers, nf = 64 features, bias, ReLU, residual.
+ * psgla_dncnn_pack_weights converts the fp32 OIHW state-dict tensors (host pointers, in layer order:
+ * in_conv, conv_list[0..depth-3], out_conv) into the library's device layout (bf16, tap-major, K-major, 128B-swizzled
+ * as the tcgen05 B operand wants it) inside packed_dev (psgla_dncnn_packed_bytes(depth) bytes). */
+size_t psgla_dncnn_packed_bytes(int depth);
+int psgla_dncnn_pack_weights(int depth, const float* const* weights_host, const float* const* biases_host,
+                             void* packed_dev, void* stream);
+/* Bytes of activation workspace for B chains of H x W (two ping-pong bf16 NHWC [B][H][W][64] buffers). */
+size_t psgla_dncnn_workspace_bytes(psgla_img_shape shape);
+
+/* "post" parameters, applied in the last layer's epilogue:
+ *   X+ = base + gain * (out_conv(h) + bias)      PSGLA: gain = alpha (restoration_algorithms.py:238, D(Y) - Y = residual)
+ *                                                PnP-ULA: gain = delta * alpha / s2 (sampling_images.py:157, :115)
+ *   if sample_dev: sample = X+                   thinning, restoration_algorithms.py:118-121 / :241-244
+ *   if mean_dev  : mean = w_old * mean + w_new * X+ ; mean2 = w_old * mean2 + w_new * X+^2   (:128-135 / :255-262,
+ *                  three rounded fp32 operations each, like the reference's eager ops) */
+typedef struct psgla_post_params {
+  float gain;
+  float w_old, w_new; /* iter_mmse/(iter_mmse+1), 1/(iter_mmse+1) as float */
+} psgla_post_params;
+
+/* One full denoiser application + post:  x_out = post(base, DnCNN residual of den_in).
+ * den_in_dev as written by a "pre" call; x_out_dev may alias the X the pre call read. */
+int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgla_img_shape shape, const void* den_in_dev,
+                              void* workspace_dev, size_t workspace_bytes, const float* base_dev,
+                              const psgla_post_params* post, float* x_out_dev, float* sample_dev, float* mean_dev,
+                              float* mean2_dev, void* stream);
+
+/* Single conv3x3 layers, exposed for parity tests against torch.nn.functional.conv2d.
+ *   cin_pad: 16 (first layer, channels 3..15 zero) or 64.   in_dev: bf16 NHWC [B][H][W][cin_pad].
+ *   out_dev: bf16 NHWC [B][H][W][64], ReLU applied if relu != 0.   layer: index into the packed weights. */
+int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer, psgla_img_shape shape, const void* in_dev,
+                        void* out_dev, int relu, void* stream);
+
+/* Layout helper: fp32 NCHW [B][3][H][W] -> bf16 NHWC [B][H][W][16]. */
+int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, void* out_dev, void* stream);
+
+/* tcgen05 descriptor self-test (development aid): runs a 128 x 64 x 64 GEMM tile whose A operand starts `row_shift`
+ * rows into a 128B-swizzled shared-memory buffer; mode selects how the shared-memory descriptor encodes that shift.
+ * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
+int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSGLA_B200_H */

@@ -1,0 +1,89 @@
+// Shared device/host helpers of libpsgla_b200: error plumbing, Philox4x32-10, Box-Muller.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/psgla_b200.h"
+
+namespace psgla {
+
+// ---------------------------------------------------------------- errors (thread-local message, int codes)
+char* last_error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define PSGLA_CUDA_TRY(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::psgla::set_error((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define PSGLA_REQUIRE(cond, ...)                                         \
+  do {                                                                   \
+    if (!(cond)) return ::psgla::set_error(PSGLA_E_BADARG, __VA_ARGS__); \
+  } while (0)
+
+inline int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+// counter = (c0, c1, c2, c3), key = (seed_lo, seed_hi).  Library convention:
+//   2D   : c0,c1 = (global step >> 1) as 64 bit, c2,c3 = global chain id
+//   image: c0 = element index / 4, c1 = iteration, c2,c3 = global chain id
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                       uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0);
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
+    const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
+#endif
+    const uint32_t lo0 = 0xD2511F53u * c0;
+    const uint32_t lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// Two uniform 32-bit words -> two independent N(0,1) (Box-Muller).  u1 in (0,1], theta = 2 pi u2.
+// Fast-math intrinsics on purpose: MUFU.LG2 / MUFU.RSQ-or-SQRT / MUFU.SIN / MUFU.COS; absolute error ~1e-6, far
+// below the Monte-Carlo resolution of any statistic the samplers feed (tests/test_gmm2d_gpu.py checks moments).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (a + 0.5) / 2^32
+  const float u2 = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));  // sqrt(-2 ln u1) = sqrt(-2 ln2 log2 u1)
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t subsequence, uint32_t ctr_lo, uint32_t ctr_hi,
+                                               float& z0, float& z1, float& z2, float& z3) {
+  uint32_t c0 = ctr_lo, c1 = ctr_hi, c2 = (uint32_t)subsequence, c3 = (uint32_t)(subsequence >> 32);
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller(c0, c1, z0, z1);
+  box_muller(c2, c3, z2, z3);
+}
+
+}  // namespace psgla

@@ -1,0 +1,32 @@
+// Error plumbing and library-level queries of libpsgla_b200.
+#include "common.cuh"
+
+namespace psgla {
+
+char* last_error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace psgla
+
+extern "C" const char* psgla_last_error(void) { return psgla::last_error_buffer(); }
+
+extern "C" int psgla_abi_version(void) { return PSGLA_ABI_VERSION; }
+
+extern "C" int psgla_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return psgla::set_error(PSGLA_E_NODEVICE, "no CUDA device");
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+    return psgla::set_error(PSGLA_E_NODEVICE, "cannot query compute capability");
+  return major * 10 + minor;
+}

@@ -1,0 +1,381 @@
+// HBM-bound stages of the image samplers: the Langevin "pre" step (data-fidelity gradient + noise) for inpainting and
+// deblurring, the circular separable blur as a shared-memory staged stencil, Philox noise, layout conversion.
+//
+// Reference arithmetic replaced here:
+//   inpainting data_grad  -mask (x - y) / sigma^2                         sampling_images.py:295
+//   deblurring data_grad  -A^T(A x - y) / sigma^2, A = circular blur      sampling_images.py:329-338
+//   PSGLA   Y = X + (delta/lambd) grad + sqrt(2) s Z                      restoration_algorithms.py:232-236
+//   PnP-ULA X + delta (-(X - proj)/lambd + grad) + sqrt(2 delta) Z        restoration_algorithms.py:104-115
+// (the denoiser term of either update is added by the last conv layer's epilogue, csrc/conv_tc.cu).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace psgla {
+
+// N(0,1) for element e (linear index within one chain's [C][H][W]) of `chain` at `iteration`:
+// Philox counter (e >> 2, iteration, chain), component e & 3.
+__device__ __forceinline__ void normal_quad(uint64_t seed, uint64_t chain, uint32_t iteration, uint32_t quad,
+                                            float (&z)[4]) {
+  philox_normal4(seed, chain, quad, iteration, z[0], z[1], z[2], z[3]);
+}
+__device__ __forceinline__ float normal_at(uint64_t seed, uint64_t chain, uint32_t iteration, uint32_t e) {
+  float z[4];
+  normal_quad(seed, chain, iteration, e >> 2, z);
+  return z[e & 3];
+}
+
+struct PreArgs {
+  int alg;
+  float gain_data, noise_scale, proj_gain, c_min, c_max;
+  unsigned long long seed;
+  long long chain_id0;
+  unsigned int iteration;
+};
+
+__device__ __forceinline__ float langevin_base(const PreArgs& a, float x, float neg_grad_unscaled, float z) {
+  // neg_grad_unscaled = mask (x - y)  resp.  A^T(A x - y); the data term is  -gain_data * that.
+  float base = fmaf(-a.gain_data, neg_grad_unscaled, x);
+  if (a.alg == PSGLA_ALG_PNPULA) {
+    const float proj = fminf(fmaxf(x, a.c_min), a.c_max);
+    base = fmaf(-a.proj_gain, x - proj, base);
+  }
+  return fmaf(a.noise_scale, z, base);
+}
+
+__device__ __forceinline__ void store_nhwc16(__nv_bfloat16* dst_pixel, float c0, float c1, float c2) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(c0, c1);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(c2, 0.f);
+  uint4* d = reinterpret_cast<uint4*>(dst_pixel);
+  d[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b), 0u, 0u);
+  d[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ------------------------------------------------------------------------------------------------ inpainting pre
+// One thread = 4 consecutive pixels of one row (all 3 channels) when W % 4 == 0, else 1 pixel.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pre_inpaint_kernel(PreArgs a, int B, int H, int W, const float* __restrict__ x, const float* __restrict__ mask,
+                   int mask_B, const float* __restrict__ y, int y_B, const float* __restrict__ noise,
+                   float* __restrict__ base, __nv_bfloat16* __restrict__ den_in) {
+  const long long plane = (long long)H * W;
+  const long long groups_per_chain = plane / VEC;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups_per_chain * B) return;
+  const int b = (int)(g / groups_per_chain);
+  const long long pix = (g % groups_per_chain) * VEC;  // first pixel (row-major) of this thread
+  float outv[3][VEC];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long e = c * plane + pix;  // element index inside the chain
+    const long long gi = ((long long)b * 3) * plane + e;
+    const long long mi = ((long long)(mask_B > 1 ? b : 0) * 3) * plane + e;
+    const long long yi = ((long long)(y_B > 1 ? b : 0) * 3) * plane + e;
+    float xv[VEC], mv[VEC], yv[VEC], zv[VEC];
+    if (VEC == 4) {
+      const float4 t0 = *reinterpret_cast<const float4*>(x + gi);
+      const float4 t1 = *reinterpret_cast<const float4*>(mask + mi);
+      const float4 t2 = *reinterpret_cast<const float4*>(y + yi);
+      xv[0] = t0.x, xv[1 % VEC] = t0.y, xv[2 % VEC] = t0.z, xv[3 % VEC] = t0.w;
+      mv[0] = t1.x, mv[1 % VEC] = t1.y, mv[2 % VEC] = t1.z, mv[3 % VEC] = t1.w;
+      yv[0] = t2.x, yv[1 % VEC] = t2.y, yv[2 % VEC] = t2.z, yv[3 % VEC] = t2.w;
+      if (noise) {
+        const float4 t3 = *reinterpret_cast<const float4*>(noise + gi);
+        zv[0] = t3.x, zv[1 % VEC] = t3.y, zv[2 % VEC] = t3.z, zv[3 % VEC] = t3.w;
+      } else {
+        float z4[4];
+        normal_quad(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e >> 2), z4);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) zv[j] = z4[j];
+      }
+    } else {
+      xv[0] = x[gi];
+      mv[0] = mask[mi];
+      yv[0] = y[yi];
+      zv[0] = noise ? noise[gi] : normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)e);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) outv[c][j] = langevin_base(a, xv[j], mv[j] * (xv[j] - yv[j]), zv[j]);
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(base + gi) = make_float4(outv[c][0], outv[c][1 % VEC], outv[c][2 % VEC], outv[c][3 % VEC]);
+    else
+      base[gi] = outv[c][0];
+    if (a.alg == PSGLA_ALG_PNPULA) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) outv[c][j] = xv[j];  // the denoiser sees X, not the partial update
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    store_nhwc16(den_in + ((long long)b * plane + pix + j) * 16, outv[0][j], outv[1][j], outv[2][j]);
+}
+
+// ------------------------------------------------------------------------------------------------ blur / deblur pre
+// Tile 32 x 32 pixels of one chain, 256 threads, each thread owns 4 consecutive pixels of a tile row.
+// Shared memory: two float planes of (32 + 4l)^2.  Separable circular blur with taps h[2l+1]:
+//   pass 1/2: r = A x - y on tile + l halo (from x on tile + 2l halo);  pass 3/4: g = A^T r on the tile (A^T = A: the
+//   taps are symmetric by construction, sampling_images.py:306-314).
+constexpr int BT = 32;
+constexpr int MAX_L = 16;
+__constant__ float c_taps[2 * MAX_L + 1];
+
+__device__ __forceinline__ int wrap(int i, int n) {
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+template <bool FULL>  // FULL: Langevin pre; else: out = A x
+__global__ void __launch_bounds__(256)
+blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, const float* __restrict__ y, int y_B,
+            const float* __restrict__ noise, float* __restrict__ out, __nv_bfloat16* __restrict__ den_in) {
+  extern __shared__ float sm[];
+  const int halo = FULL ? 2 * l : l;
+  const int SW = BT + 2 * halo;  // staged width/height
+  float* s0 = sm;
+  float* s1 = sm + SW * SW;
+  const int tiles_x = (W + BT - 1) / BT;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int b = blockIdx.y;
+  const int x0 = tx * BT, y0 = ty * BT;
+  const long long plane = (long long)H * W;
+  const int tid = threadIdx.x;
+  const int prow = tid >> 3, pcol = (tid & 7) * 4;  // this thread's 4 pixels inside the tile
+  float res[3][4];
+  float xin[3][4];
+
+  for (int c = 0; c < 3; ++c) {
+    const float* xp = x + ((long long)b * 3 + c) * plane;
+    __syncthreads();
+    for (int i = tid; i < SW * SW; i += 256) {
+      const int r = i / SW, cc = i % SW;
+      s0[i] = xp[(long long)wrap(y0 - halo + r, H) * W + wrap(x0 - halo + cc, W)];
+    }
+    __syncthreads();
+    // horizontal pass of A: s1[r][cc], cc in [0, SW - 2l)  <->  column x0 - halo + l + cc
+    const int w1 = SW - 2 * l;
+    for (int i = tid; i < SW * w1; i += 256) {
+      const int r = i / w1, cc = i % w1;
+      float acc = 0.f;
+      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s0[r * SW + cc + t], acc);
+      s1[r * SW + cc] = acc;
+    }
+    __syncthreads();
+    // vertical pass of A: s0[r][cc], r in [0, SW - 2l)
+    const int h1 = SW - 2 * l;
+    for (int i = tid; i < h1 * w1; i += 256) {
+      const int r = i / w1, cc = i % w1;
+      float acc = 0.f;
+      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s1[(r + t) * SW + cc], acc);
+      if (FULL) {
+        const float* yp = y + ((long long)(y_B > 1 ? b : 0) * 3 + c) * plane;
+        acc -= yp[(long long)wrap(y0 - l + r, H) * W + wrap(x0 - l + cc, W)];
+      }
+      s0[r * SW + cc] = acc;
+    }
+    __syncthreads();
+    if (!FULL) {
+      // s0 holds A x on the tile (halo == l  =>  h1 == w1 == BT)
+      const int gy = y0 + prow;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gx = x0 + pcol + j;
+        if (gy < H && gx < W) out[((long long)b * 3 + c) * plane + (long long)gy * W + gx] = s0[prow * SW + pcol + j];
+      }
+      continue;
+    }
+    // A^T r: horizontal then vertical on the (BT + 2l)^2 residual in s0
+    const int w2 = w1 - 2 * l;  // == BT
+    for (int i = tid; i < h1 * w2; i += 256) {
+      const int r = i / w2, cc = i % w2;
+      float acc = 0.f;
+      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s0[r * SW + cc + t], acc);
+      s1[r * SW + cc] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s1[(prow + t) * SW + pcol + j], acc);
+      res[c][j] = acc;
+    }
+  }
+  if (!FULL) return;
+
+  const int gy = y0 + prow;
+  if (gy >= H) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long rowoff = ((long long)b * 3 + c) * plane + (long long)gy * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gx = x0 + pcol + j;
+      if (gx >= W) continue;
+      const float xv = x[rowoff + gx];
+      const long long e = (long long)c * plane + (long long)gy * W + gx;
+      const float z = noise ? noise[rowoff + gx]
+                            : normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)e);
+      const float bv = langevin_base(a, xv, res[c][j], z);
+      out[rowoff + gx] = bv;
+      xin[c][j] = (a.alg == PSGLA_ALG_PNPULA) ? xv : bv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gx = x0 + pcol + j;
+    if (gx < W) store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx) * 16, xin[0][j], xin[1][j], xin[2][j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+noise_kernel(int B, long long chw, unsigned long long seed, long long chain_id0, unsigned int iteration,
+             float* __restrict__ out) {
+  const long long quads = (chw + 3) / 4;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= quads * B) return;
+  const int b = (int)(g / quads);
+  const long long q = g % quads;
+  float z[4];
+  normal_quad(seed, (unsigned long long)(chain_id0 + b), iteration, (uint32_t)q, z);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (q * 4 + j < chw) out[(long long)b * chw + q * 4 + j] = z[j];
+}
+
+__global__ void __launch_bounds__(256)
+to_nhwc16_kernel(int B, int H, int W, const float* __restrict__ x, __nv_bfloat16* __restrict__ out) {
+  const long long plane = (long long)H * W;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= plane * B) return;
+  const long long b = g / plane, pix = g % plane;
+  const float* xp = x + b * 3 * plane + pix;
+  store_nhwc16(out + g * 16, xp[0], xp[plane], xp[2 * plane]);
+}
+
+static int fill_pre(const psgla_pre_params* p, PreArgs* a) {
+  PSGLA_REQUIRE(p != nullptr, "null psgla_pre_params");
+  PSGLA_REQUIRE(p->alg == PSGLA_ALG_PSGLA || p->alg == PSGLA_ALG_PNPULA, "alg=%d is not a PSGLA_ALG_* value", p->alg);
+  PSGLA_REQUIRE(p->iteration >= 0 && p->iteration <= 0xffffffffLL && p->chain_id0 >= 0, "iteration / chain id out of range");
+  a->alg = p->alg;
+  a->gain_data = p->gain_data;
+  a->noise_scale = p->noise_scale;
+  a->proj_gain = p->proj_gain;
+  a->c_min = p->c_min;
+  a->c_max = p->c_max;
+  a->seed = p->seed;
+  a->chain_id0 = p->chain_id0;
+  a->iteration = (unsigned int)p->iteration;
+  return PSGLA_OK;
+}
+
+static int check_img(const psgla_img_shape& s) {
+  PSGLA_REQUIRE(s.B > 0 && s.H > 0 && s.W > 0 && s.C == 3, "image shape must be [B>0][3][H>0][W>0], got [%d][%d][%d][%d]",
+                s.B, s.C, s.H, s.W);
+  PSGLA_REQUIRE((long long)s.C * s.H * s.W < (1LL << 32), "one chain must have fewer than 2^32 elements");
+  return PSGLA_OK;
+}
+
+static int upload_taps(const float* h1d_host, int l, cudaStream_t st) {
+  PSGLA_REQUIRE(h1d_host != nullptr && l >= 0 && l <= MAX_L, "blur half-width l must be in 0..%d (got %d)", MAX_L, l);
+  PSGLA_CUDA_TRY(cudaMemcpyToSymbolAsync(c_taps, h1d_host, sizeof(float) * (2 * l + 1), 0, cudaMemcpyHostToDevice, st));
+  return PSGLA_OK;
+}
+
+}  // namespace psgla
+
+using namespace psgla;
+
+extern "C" int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape s, const float* x_dev,
+                                     const float* mask_dev, int mask_B, const float* y_dev, int y_B,
+                                     const float* noise_dev, float* base_dev, void* den_in_dev, void* stream) {
+  PreArgs a;
+  int rc = fill_pre(p, &a);
+  if (rc) return rc;
+  rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(x_dev && mask_dev && y_dev && base_dev && den_in_dev, "psgla_img_pre_inpaint: null pointer");
+  PSGLA_REQUIRE((mask_B == 1 || mask_B == s.B) && (y_B == 1 || y_B == s.B), "mask_B / y_B must be 1 or B");
+  const long long plane = (long long)s.H * s.W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plane % 4 == 0) {
+    const long long n = plane / 4 * s.B;
+    pre_inpaint_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, s.B, s.H, s.W, x_dev, mask_dev, mask_B, y_dev,
+                                                                      y_B, noise_dev, base_dev,
+                                                                      (__nv_bfloat16*)den_in_dev);
+  } else {
+    const long long n = plane * s.B;
+    pre_inpaint_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, s.B, s.H, s.W, x_dev, mask_dev, mask_B, y_dev,
+                                                                      y_B, noise_dev, base_dev,
+                                                                      (__nv_bfloat16*)den_in_dev);
+  }
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+template <bool FULL>
+static int launch_blur(const PreArgs& a, psgla_img_shape s, int l, const float* x, const float* y, int y_B,
+                       const float* noise, float* out, void* den_in, cudaStream_t st) {
+  const int halo = FULL ? 2 * l : l;
+  const int SW = BT + 2 * halo;
+  const size_t smem = (size_t)2 * SW * SW * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(blur_kernel<FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int tiles = ((s.W + BT - 1) / BT) * ((s.H + BT - 1) / BT);
+  blur_kernel<FULL><<<dim3(tiles, s.B), 256, smem, st>>>(a, s.B, s.H, s.W, l, x, y, y_B, noise, out,
+                                                        (__nv_bfloat16*)den_in);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_img_pre_deblur(const psgla_pre_params* p, psgla_img_shape s, const float* x_dev,
+                                    const float* h1d_host, int l, const float* y_dev, int y_B, const float* noise_dev,
+                                    float* base_dev, void* den_in_dev, void* stream) {
+  PreArgs a;
+  int rc = fill_pre(p, &a);
+  if (rc) return rc;
+  rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(x_dev && y_dev && base_dev && den_in_dev, "psgla_img_pre_deblur: null pointer");
+  PSGLA_REQUIRE(x_dev != base_dev, "psgla_img_pre_deblur: base must not alias x (the stencil reads neighbours)");
+  PSGLA_REQUIRE(y_B == 1 || y_B == s.B, "y_B must be 1 or B");
+  rc = upload_taps(h1d_host, l, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_blur<true>(a, s, l, x_dev, y_dev, y_B, noise_dev, base_dev, den_in_dev, (cudaStream_t)stream);
+}
+
+extern "C" int psgla_img_blur(psgla_img_shape s, const float* x_dev, const float* h1d_host, int l, float* out_dev,
+                              void* stream) {
+  int rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(x_dev && out_dev && x_dev != out_dev, "psgla_img_blur: null or aliased pointer");
+  rc = upload_taps(h1d_host, l, (cudaStream_t)stream);
+  if (rc) return rc;
+  PreArgs a{};
+  return launch_blur<false>(a, s, l, x_dev, nullptr, 1, nullptr, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int psgla_img_noise(psgla_img_shape s, uint64_t seed, int64_t chain_id0, int64_t iteration, float* out_dev,
+                               void* stream) {
+  int rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(out_dev && iteration >= 0 && iteration <= 0xffffffffLL && chain_id0 >= 0, "psgla_img_noise: bad argument");
+  const long long chw = (long long)s.C * s.H * s.W;
+  const long long n = (chw + 3) / 4 * s.B;
+  noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s.B, chw, seed, chain_id0,
+                                                                             (unsigned int)iteration, out_dev);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_img_to_nhwc16(psgla_img_shape s, const float* x_dev, void* out_dev, void* stream) {
+  int rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(x_dev && out_dev, "psgla_img_to_nhwc16: null pointer");
+  const long long n = (long long)s.H * s.W * s.B;
+  to_nhwc16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s.B, s.H, s.W, x_dev,
+                                                                                 (__nv_bfloat16*)out_dev);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}

@@ -1,0 +1,108 @@
+"""DnCNN denoiser running as tcgen05 implicit-GEMM convolutions (csrc/conv_tc.cu).
+
+Mirrors ``deepinv.models.DnCNN(in_channels=3, out_channels=3, pretrained=..., device=...)`` as the reference constructs
+it (sampling_images.py:130) and calls it (``denoiser.forward(x, sigma)``, restoration_algorithms.py:238): depth 20,
+64 features, 3x3, bias, ReLU, residual output, ``sigma`` ignored.  Weights come from a deepinv-style state dict
+(keys ``in_conv``, ``conv_list.i``, ``out_conv``) -- a checkpoint path, a dict, or ``None`` for seeded random init.
+Activations are bf16 with fp32 accumulation; the input / output images stay fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+__all__ = ["DnCNN", "random_dncnn_state_dict"]
+
+
+def random_dncnn_state_dict(seed=0, depth=20, nf=64, scale=1.0):
+    """Deterministic random-init DnCNN state dict (uniform +-1/sqrt(fan_in) like nn.Conv2d's default), on the CPU."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, cout, cin):
+        bound = scale / math.sqrt(cin * 9)
+        sd[name + ".weight"] = (torch.rand((cout, cin, 3, 3), generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * 0.01
+
+    conv("in_conv", nf, 3)
+    for i in range(depth - 2):
+        conv("conv_list.%d" % i, nf, nf)
+    conv("out_conv", 3, nf)
+    return sd
+
+
+class DnCNN:
+    def __init__(self, in_channels=3, out_channels=3, depth=20, bias=True, nf=64, pretrained=None, device=None):
+        torch_ = _lib.require_cuda()
+        if in_channels != 3 or out_channels != 3 or nf != 64:
+            raise ValueError("the sm_100a conv path is built for colour DnCNN: in=out=3 channels, nf=64")
+        if depth < 2:
+            raise ValueError("depth must be >= 2")
+        self.depth = int(depth)
+        self.device = torch_.device("cuda", torch_.cuda.current_device()) if device is None else torch_.device(device)
+        if pretrained is None:
+            sd = random_dncnn_state_dict(0, depth, nf)
+        elif isinstance(pretrained, str):
+            sd = torch_.load(pretrained, map_location="cpu")
+        else:
+            sd = pretrained
+        names = ["in_conv"] + ["conv_list.%d" % i for i in range(depth - 2)] + ["out_conv"]
+        missing = [n for n in names if n + ".weight" not in sd]
+        if missing:
+            raise KeyError("state dict lacks %s" % missing[:3])
+        self.state_dict_fp32 = {k: v.detach().to("cpu", torch_.float32).contiguous() for k, v in sd.items()}
+        ws = [self.state_dict_fp32[n + ".weight"] for n in names]
+        expect = [(nf, 3, 3, 3)] + [(nf, nf, 3, 3)] * (depth - 2) + [(3, nf, 3, 3)]
+        for w, e, n in zip(ws, expect, names):
+            if tuple(w.shape) != e:
+                raise ValueError("%s.weight has shape %s, expected %s" % (n, tuple(w.shape), e))
+        bs = [self.state_dict_fp32.get(n + ".bias") if bias else None for n in names]
+        lib = _lib.lib()
+        self.packed = torch_.empty(lib.psgla_dncnn_packed_bytes(self.depth), dtype=torch_.uint8, device=self.device)
+        FP = C.POINTER(C.c_float)
+        warr = (FP * depth)(*[C.cast(w.data_ptr(), FP) for w in ws])
+        barr = (FP * depth)(*[C.cast(b.data_ptr(), FP) if b is not None else FP() for b in bs])
+        with torch_.cuda.device(self.device):
+            _lib.check(lib.psgla_dncnn_pack_weights(self.depth, warr, barr, _lib.ptr(self.packed),
+                                                    _lib.stream_ptr(self.device)), "psgla_dncnn_pack_weights")
+        self._ws = None
+        self._den_in = None
+
+    # workspace shared by every call with the same shape
+    def buffers(self, shape: "_lib.ImgShape"):
+        need = _lib.lib().psgla_dncnn_workspace_bytes(shape)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        n_in = shape.B * shape.H * shape.W * 16
+        if self._den_in is None or self._den_in.numel() < n_in:
+            self._den_in = torch.empty(n_in, dtype=torch.bfloat16, device=self.device)
+        return self._ws, self._den_in
+
+    def residual_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None):
+        ws, _ = self.buffers(shape)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().psgla_dncnn_residual_post(self.depth, _lib.ptr(self.packed), shape, _lib.ptr(den_in),
+                                                      _lib.ptr(ws), ws.numel(), _lib.ptr(base), C.byref(post),
+                                                      _lib.ptr(x_out), _lib.ptr(sample), _lib.ptr(mean), _lib.ptr(mean2),
+                                                      _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_dncnn_residual_post")
+
+    def forward(self, x, sigma=None):
+        """D(x) = x + R(x), fp32 [B,3,H,W] in and out (``sigma`` ignored, as in deepinv's DnCNN)."""
+        if not x.is_cuda:
+            raise RuntimeError("DnCNN.forward needs a CUDA tensor: there is no CPU path")
+        x = x.to(torch.float32).contiguous()
+        shape = _lib.ImgShape(int(x.shape[0]), 3, int(x.shape[2]), int(x.shape[3]))
+        _, den_in = self.buffers(shape)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().psgla_img_to_nhwc16(shape, _lib.ptr(x), _lib.ptr(den_in), _lib.stream_ptr(self.device)),
+                       "psgla_img_to_nhwc16")
+        self.residual_post(shape, den_in, x, _lib.PostParams(1.0, 0.0, 1.0), out)
+        return out
+
+    __call__ = forward

@@ -1,0 +1,192 @@
+"""Drop-in for the Langevin samplers of the reference's ``restoration_algorithms.py``: ``psgla`` (:163-285) and
+``pnpula`` (:38-160; ``pnp_ula`` is the script's ``--alg`` spelling, exported as an alias).
+
+Same positional / keyword arguments and the same return triple ``(Xlist, Xlist_mmse, Xlist_mmse2)`` of device
+tensors.  Per iteration the host issues two C-ABI calls: the fused Langevin "pre" kernel and the DnCNN layer chain
+whose last layer's epilogue applies the denoiser term, thins samples and updates the running moments.
+Extra keyword-only arguments:
+  noise          tensor (n_iter, *init.shape) of N(0,1) draws to replay (e.g. the reference's torch.randn stream)
+  rng            "philox" (default: in-kernel Philox4x32-10, keyed by seed / chain id / iteration) or "torch"
+                 (draw ``torch.randn(im_shape, generator=Generator(device).manual_seed(seed))`` per iteration exactly
+                 like the reference and replay it)
+  n_chains       run that many independent chains of the same problem (init broadcast); outputs gain a leading
+                 chain axis
+  chain_id0      global id of the first chain (Philox subsequence) when chains are sharded over GPUs
+The data term must be an ``InpaintingDataGrad`` / ``DeblurDataGrad`` and the denoiser a ``psgla_b200.DnCNN``
+(``prior_grad`` a ``PriorGrad`` wrapping one); opaque callables raise ``TypeError`` -- there is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .denoisers import DnCNN
+from .operators import DeblurDataGrad, InpaintingDataGrad, PriorGrad
+
+__all__ = ["psgla", "pnpula", "pnp_ula"]
+
+
+def _f(v):
+    return float(v.item()) if isinstance(v, torch.Tensor) else float(v)
+
+
+class _Run:
+    """State shared by both samplers: buffers, thinning, running moments (restoration_algorithms.py:118-144)."""
+
+    def __init__(self, init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0):
+        _lib.require_cuda()
+        if not isinstance(data_grad, (InpaintingDataGrad, DeblurDataGrad)):
+            raise TypeError("data_grad must be an InpaintingDataGrad or DeblurDataGrad (structured callable); an opaque "
+                            "callable cannot be fused into the CUDA kernels and there is no eager fallback")
+        if not isinstance(denoiser, DnCNN):
+            raise TypeError("denoiser must be a psgla_b200.DnCNN")
+        if seed is None and noise is None:
+            raise ValueError("seed=None: the reference fails with UnboundLocalError here "
+                             "(restoration_algorithms.py:211-213,232); pass a seed or a noise tensor")
+        if not init.is_cuda:
+            raise RuntimeError("init must be a CUDA tensor: there is no CPU path")
+        self.dg, self.den = data_grad, denoiser
+        self.device = init.device
+        x = init.detach().to(torch.float32)
+        if x.dim() == 3:
+            x = x[None]
+        self.squeeze = n_chains is None and x.shape[0] == 1
+        B = int(n_chains) if n_chains is not None else int(x.shape[0])
+        self.X = x.expand(B, -1, -1, -1).contiguous().clone() if x.shape[0] != B else x.contiguous().clone()
+        self.shape = _lib.ImgShape(B, 3, int(x.shape[2]), int(x.shape[3]))
+        self.base = torch.empty_like(self.X)
+        _, self.den_in = denoiser.buffers(self.shape)
+        self.n_iter, self.n_inter = int(n_iter), int(n_inter)
+        self.n_inter_mmse = int(n_inter if n_inter_mmse is None else n_inter_mmse)
+        if self.n_inter < 1:
+            raise ZeroDivisionError("integer modulo by zero (n_inter must be >= 1, as in the reference)")
+        n_samples = (self.n_iter + self.n_inter - 1) // self.n_inter
+        self.samples = torch.empty((max(n_samples, 1),) + tuple(self.X.shape), dtype=torch.float32, device=self.device)
+        self.mean = torch.zeros_like(self.X)
+        self.mean2 = torch.zeros_like(self.X)
+        self.Xlist, self.Xlist_mmse, self.Xlist_mmse2 = [], [], []
+        self.iter_mmse = 0
+        self.seed = 0 if seed is None else int(seed)
+        self.chain_id0 = int(chain_id0)
+        self.noise = noise
+        self.gen = None
+        if noise is None and rng == "torch":
+            self.gen = torch.Generator(device=self.device)
+            self.gen.manual_seed(self.seed)
+        elif noise is None and rng != "philox":
+            raise ValueError("rng must be 'philox' or 'torch'")
+        if noise is not None and tuple(noise.shape[1:]) != tuple(self.X.shape) and not (
+                self.X.shape[0] == 1 and tuple(noise.shape[1:]) == tuple(self.X.shape[1:])):
+            raise ValueError("noise must have shape (n_iter, *init.shape)")
+        if isinstance(data_grad, DeblurDataGrad):
+            self.y = data_grad.y.to(self.device)
+            self.mask = None
+        else:
+            self.y = data_grad.y.to(self.device).expand(-1, 3, -1, -1).contiguous()
+            self.mask = data_grad.mask.to(self.device).expand(-1, 3, -1, -1).contiguous()
+
+    def _out(self, t):
+        return t[0] if self.squeeze else t
+
+    def z_for(self, i):
+        if self.noise is not None:
+            return self.noise[i].to(self.device, torch.float32).reshape(self.X.shape).contiguous()
+        if self.gen is not None:
+            return torch.randn(self.X.shape, generator=self.gen, dtype=torch.float32, device=self.device)
+        return None
+
+    def pre(self, i, pre: "_lib.PreParams"):
+        z = self.z_for(i)
+        pre.seed, pre.chain_id0, pre.iteration = self.seed, self.chain_id0, i
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            if self.mask is not None:
+                rc = lib.psgla_img_pre_inpaint(C.byref(pre), self.shape, _lib.ptr(self.X), _lib.ptr(self.mask),
+                                               int(self.mask.shape[0]), _lib.ptr(self.y), int(self.y.shape[0]),
+                                               _lib.ptr(z), _lib.ptr(self.base), _lib.ptr(self.den_in), st)
+                _lib.check(rc, "psgla_img_pre_inpaint")
+            else:
+                rc = lib.psgla_img_pre_deblur(C.byref(pre), self.shape, _lib.ptr(self.X), self.dg._taps_c, self.dg.l,
+                                              _lib.ptr(self.y), int(self.y.shape[0]), _lib.ptr(z), _lib.ptr(self.base),
+                                              _lib.ptr(self.den_in), st)
+                _lib.check(rc, "psgla_img_pre_deblur")
+
+    def post(self, i, gain):
+        k = self.iter_mmse
+        post = _lib.PostParams(float(gain), float(np.float32(k / (k + 1))), float(np.float32(1 / (k + 1))))
+        sample = self.samples[i // self.n_inter] if i % self.n_inter == 0 else None
+        self.den.residual_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2)
+        if sample is not None:
+            self.Xlist.append(self._out(sample))
+        # window bookkeeping exactly as restoration_algorithms.py:128-144 / :255-271
+        if self.iter_mmse <= self.n_inter_mmse - 1:
+            self.iter_mmse += 1
+        else:
+            self.Xlist_mmse.append(self._out(self.mean.clone()))
+            self.Xlist_mmse2.append(self._out(self.mean2.clone()))
+            self.iter_mmse = 0  # the next update has w_old = 0, which restarts the window without a memset
+
+
+def _save_online(path, name, i, run, extra):
+    # restoration_algorithms.py:146-158 / :273-283 (the PNG previews need matplotlib and are not reproduced)
+    d = {"Samples": run.Xlist, "Mmse": run.Xlist_mmse, "Mmse2": run.Xlist_mmse2, "n_iter": run.n_iter}
+    d.update(extra)
+    torch.save(d, (path or "") + "/" + (name or "") + "_sampling.pth")
+
+
+def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
+          n_inter_mmse=1000, seed=None, device=None, path=None, save_images_online=False, name=None, *, noise=None,
+          rng="philox", n_chains=None, chain_id0=0):
+    """PSGLA (restoration_algorithms.py:163-285):  Y = X + (delta/lambd) data_grad(X) + sqrt(2) sig Z;
+    X = (1 - alpha) Y + alpha D(Y).  Returns (Xlist, Xlist_mmse, Xlist_mmse2)."""
+    run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    alpha_f, lambd_f = _f(alpha), _f(lambd)
+    delta32 = float(np.float32(delta))
+    sig32 = float(np.float32(sig_float))
+    print("delta = {}, sigma = {}".format(delta, sig_float))
+    K = int(run.n_iter / 10)
+    pre = _lib.PreParams()
+    pre.alg = _lib.ALG_PSGLA
+    pre.gain_data = (delta32 / lambd_f) / run.dg.sigma2
+    pre.noise_scale = float(np.float32(np.float32(np.sqrt(2)) * np.float32(sig32)))
+    pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0
+    for i in range(run.n_iter):
+        run.pre(i, pre)
+        run.post(i, alpha_f)  # (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
+        if i % K == 0 and save_images_online:  # ZeroDivisionError for n_iter < 10, as in the reference (:246)
+            _save_online(path, name, i, run, {"lambda": lambd, "delta": delta})
+    return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
+
+
+def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
+           device=None, c_min=-1, c_max=2, path=None, save_images_online=False, name=None, *, noise=None, rng="philox",
+           n_chains=None, chain_id0=0):
+    """PnP-ULA (restoration_algorithms.py:38-160):
+    X+ = X + delta (prior_grad(X) - (X - proj_[c_min,c_max] X)/lambd + data_grad(X)) + sqrt(2 delta) Z."""
+    if not isinstance(prior_grad, PriorGrad):
+        raise TypeError("prior_grad must be a PriorGrad(denoiser, alpha, s1, s2) structured callable")
+    run = _Run(init, data_grad, prior_grad.denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    delta_f, lambd_f = _f(delta), _f(lambd)
+    print("delta = {}".format(delta.float() if isinstance(delta, torch.Tensor) else delta))
+    K = int(run.n_iter / 10)
+    pre = _lib.PreParams()
+    pre.alg = _lib.ALG_PNPULA
+    pre.gain_data = delta_f / run.dg.sigma2
+    pre.noise_scale = float(np.float32(math.sqrt(2 * delta_f)))
+    pre.proj_gain = delta_f / lambd_f
+    pre.c_min, pre.c_max = float(c_min), float(c_max)
+    gain = delta_f * prior_grad.alpha / prior_grad.s2
+    for i in range(run.n_iter):
+        run.pre(i, pre)
+        run.post(i, gain)
+        if i % K == 0 and save_images_online:
+            _save_online(path, name, i, run, {"c_min": c_min, "c_max": c_max, "lambda": lambd, "delta": delta})
+    return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
+
+
+pnp_ula = pnpula
