@@ -6,6 +6,7 @@ C ABI (include/psgla_b200.h), no CPU fallback.  Import as ``psgla_b200`` (see ps
 directory name carries the reference's name and is not a Python identifier).
 """
 from . import _lib  # noqa: F401
+from . import dist  # noqa: F401
 from .denoisers import DnCNN, random_dncnn_state_dict  # noqa: F401
 from .operators import (DeblurDataGrad, InpaintingDataGrad, PriorGrad, blur_taps, make_deblurring,  # noqa: F401
                         make_inpainting)

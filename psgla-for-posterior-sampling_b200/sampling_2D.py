@@ -52,6 +52,8 @@ class GMMChains:
 
     def __init__(self, alg, y, delta, A, sigma, denoiser, alpha, epsilon=1.0, n_chains=1, x0=None, seed=0,
                  chain_id0=0, dtype="float32", device=None):
+        if not isinstance(denoiser, GMMDenoiser):
+            _problem(0, y, delta, A, sigma, denoiser, alpha, epsilon)  # raises the TypeError
         torch = _lib.require_cuda()
         self.torch = torch
         self.alg = {"psgla": _lib.ALG_PSGLA, "snopnp_ula": _lib.ALG_PSGLA, "pnp_ula": _lib.ALG_PNPULA}[alg.lower()] \

@@ -1,0 +1,85 @@
+"""not-gpu: host-side logic of the product package (posterior constants, metrics, sharding, operators' callable form)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import psgla_b200 as P
+from oracle import gmm2d_oracle as o
+from oracle import image_oracle as io_
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gmm2d_golden.json")))
+
+
+def test_priors_match_reference_table():
+    for name in o.PRIOR_NAMES:
+        a, b = P.gaussian_mixt_example(name), o.gaussian_mixt_example(name)
+        for x, y in zip(a, b):
+            assert np.allclose(np.asarray(x, dtype=float), np.asarray(y, dtype=float))
+
+
+def test_posterior_constants_golden():
+    for g in GOLD["posterior"]:
+        mu, Sig, pi = P.gaussian_mixt_example(g["prior"])
+        m, S, p = P.constantes_conditionnal_prob(np.eye(2), np.array(g["y"]), 1, mu, Sig, pi)
+        assert np.allclose(np.array(m), np.array(g["mu"]), atol=1e-10)
+        assert np.allclose(np.array(S), np.array(g["Sigma"]), atol=1e-10)
+        assert np.allclose(p, g["p"], atol=1e-10)
+
+
+def test_sample_posterior_same_stream_as_oracle():
+    mu, Sig, pi = P.gaussian_mixt_example("disymmetric_gaussians")
+    y = np.array([0, -2])
+    np.random.seed(3)
+    a = P.sample_posterior(np.eye(2), y, 1, 400, mu, Sig, pi)
+    np.random.seed(3)
+    b = o.sample_posterior(np.eye(2), y, 1, 400, mu, Sig, pi)
+    assert np.allclose(a, b, atol=1e-10)
+
+
+def test_wasserstein_matches_oracle_and_translation():
+    rng = np.random.default_rng(1)
+    a, b = rng.standard_normal((300, 2)), rng.standard_normal((300, 2)) + 1.0
+    w1 = P.Wasserstein_distance(a, b, rng=np.random.default_rng(5))
+    w2 = o.wasserstein_distance(a, b, rng=np.random.default_rng(5))
+    assert w1 == pytest.approx(w2, rel=1e-12)
+    assert P.Wasserstein_distance(a, a + np.array([0.0, 2.0]), rng=np.random.default_rng(0)) == pytest.approx(4.0, abs=0.5)
+    assert P.sliced_wasserstein_distance(a, a) == 0.0
+
+
+def test_shard_range_tiles():
+    for n in (0, 1, 7, 68, 10 ** 6):
+        for ws in (1, 2, 3, 8):
+            blocks = [P.dist.shard_range(n, r, ws) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_structured_operators_are_callable_like_the_reference_closures():
+    torch.manual_seed(0)
+    im = torch.rand(1, 3, 12, 12)
+    ref = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    assert torch.equal(mask, ref["mask"]) and torch.equal(y, ref["y"]) and torch.equal(init, ref["init"])
+    x = torch.rand(1, 3, 12, 12)
+    assert torch.equal(dg(x), ref["data_grad"](x))
+    refd = io_.make_deblurring(im, l=2, blur_type="gaussian", si=1.0)
+    dd, initd, yd = P.make_deblurring(im, l=2, blur_type="gaussian", si=1.0)
+    assert torch.allclose(yd, refd["y"], atol=1e-6)
+    assert torch.allclose(dd(x), refd["data_grad"](x), rtol=1e-4, atol=1e-2)
+    # the reference's own psgla accepts the structured callable (CPU, tiny)
+    den = io_.DnCNN(depth=3, nf=4)
+    a = io_.psgla(init, dg, den, torch.tensor(1.0), torch.tensor(5.0), 2 / 255, (2 / 255) ** 2, n_iter=3, n_inter=1, n_inter_mmse=1, seed=0)
+    b = io_.psgla(ref["init"], ref["data_grad"], den, torch.tensor(1.0), torch.tensor(5.0), 2 / 255, (2 / 255) ** 2, n_iter=3, n_inter=1, n_inter_mmse=1, seed=0)
+    assert all(torch.equal(u, v) for u, v in zip(a[0], b[0]))
+
+
+def test_opaque_callables_are_rejected():
+    with pytest.raises(TypeError):
+        P.pnpula(torch.zeros(1, 3, 8, 8), lambda x: x, lambda x: x, 1e-6, 1e-6, seed=0)
+    with pytest.raises(ValueError):
+        P.DeblurDataGrad(np.array([0.2, 0.3, 0.5]), 1, torch.zeros(1, 3, 4, 4), 1.0)  # non-symmetric taps

@@ -1,0 +1,290 @@
+"""-m gpu: image path through the C ABI against the plain-PyTorch fp32 oracle (oracle/image_oracle.py).
+
+Stated tolerances
+  * elementwise / stencil kernels (fp32): 1e-5 relative to the tensor's scale (they fold constants, e.g. one multiply by
+    (delta/lambd)/sigma^2 instead of the reference's divide-then-multiply);
+  * one conv layer, bf16 operands with fp32 accumulation, bf16 output: <= 1 bf16 ulp of the output scale;
+  * DnCNN residual (20 layers, bf16 activations): <= 1e-2 relative L2 error of the residual;
+  * sampler iterates under replayed noise, bf16 denoiser vs fp32 oracle: <= 2e-2 abs over the first 50 iterations
+    (images live in [0,1]); thinning / window bookkeeping must match exactly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import psgla_b200 as P
+from oracle import image_oracle as io_
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return io_.make_dncnn_weights(seed=0, n_power_iter=10, spatial=16)
+
+
+@pytest.fixture(scope="module")
+def nets(weights):
+    den = P.DnCNN(pretrained=weights)
+    net = io_.DnCNN().cuda()
+    net.load_state_dict(weights)
+    return den, net.eval()
+
+
+def test_umma_descriptor_selftest():
+    lib = P._lib.lib()
+    torch.manual_seed(0)
+    a = torch.randn(136, 64, device="cuda").to(torch.bfloat16).contiguous()
+    b = torch.randn(64, 64, device="cuda").to(torch.bfloat16).contiguous()
+    for shift in (0, 1, 2, 5, 8):
+        d = torch.zeros(128, 64, device="cuda")
+        P._lib.check(lib.psgla_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), shift, 0, None), "selftest")
+        torch.cuda.synchronize()
+        ref = a[shift:shift + 128].float() @ b.float().t()
+        assert (d - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,layer", [(1, 8, 128, 1), (2, 40, 256, 5), (1, 33, 200, 3), (3, 5, 17, 2), (1, 1, 1, 4),
+                                         (1, 8, 128, 0), (2, 37, 150, 0), (1, 8, 128, 19), (2, 37, 150, 19), (1, 321, 481, 7)])
+def test_conv_layer_against_torch(B, H, W, layer):
+    depth = 20
+    lib = P._lib.lib()
+    sd = P.random_dncnn_state_dict(3, depth, scale=3.0)
+    den = P.DnCNN(depth=depth, pretrained=sd)
+    names = ["in_conv"] + ["conv_list.%d" % i for i in range(depth - 2)] + ["out_conv"]
+    w, bias = sd[names[layer] + ".weight"].cuda(), sd[names[layer] + ".bias"].cuda()
+    cin = w.shape[1]
+    x = torch.randn(B, cin, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).to(torch.bfloat16)
+    cpad = 16 if layer == 0 else 64
+    xin = torch.zeros(B, H, W, cpad, device="cuda", dtype=torch.bfloat16)
+    xin[..., :cin] = x.permute(0, 2, 3, 1)
+    ref = F.conv2d(x.float(), w.to(torch.bfloat16).float(), bias, padding=1)
+    shape = P._lib.ImgShape(B, 3, H, W)
+    if layer == depth - 1:
+        out = torch.full((B, 3, H, W), float("nan"), device="cuda")
+        P._lib.check(lib.psgla_conv3x3_layer(den.packed.data_ptr(), depth, layer, shape, xin.data_ptr(), out.data_ptr(), 0, None), "conv")
+        torch.cuda.synchronize()
+        assert (out - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    else:
+        out = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        P._lib.check(lib.psgla_conv3x3_layer(den.packed.data_ptr(), depth, layer, shape, xin.data_ptr(), out.data_ptr(), 1, None), "conv")
+        torch.cuda.synchronize()
+        got, ref = out.float().permute(0, 3, 1, 2), ref.relu()
+        assert (got - ref).abs().max().item() <= 2 ** -8 * max(1.0, ref.abs().max().item()) * 1.01
+
+
+def test_dncnn_forward_against_fp32_oracle(nets):
+    den, net = nets
+    for shape in ((2, 3, 64, 96), (1, 3, 130, 70)):
+        x = torch.rand(*shape, device="cuda")
+        with torch.no_grad():
+            ref = net(x)
+        got = den.forward(x, 2 / 255)
+        r_ref, r_got = ref - x, got - x
+        assert ((r_got - r_ref).norm() / r_ref.norm()).item() < 1e-2
+        assert (got - ref).abs().max().item() < 1e-3
+
+
+def test_blur_against_reference_formulation():
+    torch.manual_seed(0)
+    im = torch.rand(2, 3, 45, 70, device="cuda")
+    for l, bt in ((4, "uniform"), (2, "gaussian"), (7, "gaussian"), (0, "uniform")):
+        h = P.blur_taps(l, bt, 1.3).reshape(-1)
+        op = P.DeblurDataGrad(h, l, torch.zeros_like(im), 1.0)
+        got = op.A(im)
+        want = op.A(im.cpu()).cuda()  # the reference's pad-circular + depthwise conv2d formulation (sampling_images.py:329)
+        assert (got - want).abs().max().item() < 1e-5
+
+
+def _pre_inputs(B, H, W, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.rand(B, 3, H, W, device="cuda", generator=g) * 1.6 - 0.3
+    z = torch.randn(B, 3, H, W, device="cuda", generator=g)
+    im = torch.rand(1, 3, H, W, device="cuda", generator=g)
+    return x, z, im
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (33, 47), (64, 128)])
+@pytest.mark.parametrize("alg", ["psgla", "pnp_ula"])
+def test_pre_inpaint_against_oracle(H, W, alg):
+    lib = P._lib.lib()
+    B = 3
+    x, z, im = _pre_inputs(B, H, W)
+    dg, init, y, mask = P.make_inpainting(im)
+    pre = P._lib.PreParams()
+    if alg == "psgla":
+        prm = io_.resolve_params("psgla")
+        pre.alg, pre.gain_data, pre.noise_scale = 0, (prm["delta"] / prm["lambd"]) / dg.sigma2, float(np.sqrt(2) * prm["s"])
+        want = x + (prm["delta"] / prm["lambd"]) * dg(x) + float(np.sqrt(2) * prm["s"]) * z
+        den_want = want
+    else:
+        prm = io_.resolve_params("pnp_ula", s=5.0)
+        pre.alg, pre.gain_data, pre.noise_scale = 1, prm["delta"] / dg.sigma2, float(np.sqrt(2 * prm["delta"]))
+        pre.proj_gain, pre.c_min, pre.c_max = prm["delta"] / prm["lambd"], 0.1, 0.9
+        proj = x.clamp(0.1, 0.9)
+        want = x + prm["delta"] * (-(x - proj) / prm["lambd"] + dg(x)) + float(np.sqrt(2 * prm["delta"])) * z
+        den_want = x
+    base = torch.empty_like(x)
+    den_in = torch.full((B, H, W, 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    m3, y3 = mask.expand(-1, 3, -1, -1).contiguous(), y.contiguous()
+    P._lib.check(lib.psgla_img_pre_inpaint(pre, P._lib.ImgShape(B, 3, H, W), x.data_ptr(), m3.data_ptr(), 1, y3.data_ptr(), 1,
+                                           z.data_ptr(), base.data_ptr(), den_in.data_ptr(), None), "pre")
+    torch.cuda.synchronize()
+    assert (base - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    assert torch.equal(den_in[..., :3].float(), den_want.permute(0, 2, 3, 1).to(torch.bfloat16).float()) or \
+        (den_in[..., :3].float() - den_want.permute(0, 2, 3, 1)).abs().max().item() < 2 ** -7
+    assert torch.count_nonzero(den_in[..., 3:]).item() == 0
+
+
+@pytest.mark.parametrize("H,W,l,bt", [(32, 32, 4, "uniform"), (45, 70, 2, "gaussian"), (64, 96, 4, "gaussian")])
+def test_pre_deblur_against_oracle(H, W, l, bt):
+    lib = P._lib.lib()
+    B = 2
+    x, z, im = _pre_inputs(B, H, W, seed=2)
+    dd, init, y = P.make_deblurring(im, l=l, blur_type=bt, si=1.0)
+    prm = io_.resolve_params("psgla")
+    pre = P._lib.PreParams()
+    pre.alg, pre.gain_data, pre.noise_scale = 0, (prm["delta"] / prm["lambd"]) / dd.sigma2, float(np.sqrt(2) * prm["s"])
+    ref_op = P.DeblurDataGrad(dd.h1d, l, y.cpu(), dd.sigma2)  # CPU tensors -> the reference's conv2d formulation
+    want = (x.cpu() + (prm["delta"] / prm["lambd"]) * ref_op(x.cpu()) + float(np.sqrt(2) * prm["s"]) * z.cpu()).cuda()
+    base = torch.empty_like(x)
+    den_in = torch.empty((B, H, W, 16), device="cuda", dtype=torch.bfloat16)
+    P._lib.check(lib.psgla_img_pre_deblur(pre, P._lib.ImgShape(B, 3, H, W), x.data_ptr(), dd._taps_c, l, y.data_ptr(), 1,
+                                          z.data_ptr(), base.data_ptr(), den_in.data_ptr(), None), "pre_deblur")
+    torch.cuda.synchronize()
+    assert (base - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    assert (den_in[..., :3].float() - want.permute(0, 2, 3, 1)).abs().max().item() < 2 ** -7 * max(1.0, want.abs().max().item())
+
+
+def test_image_philox_noise_matches_pre_kernel():
+    lib = P._lib.lib()
+    for H, W in ((32, 64), (33, 47)):
+        B = 2
+        shape = P._lib.ImgShape(B, 3, H, W)
+        z = torch.empty(B, 3, H, W, device="cuda")
+        P._lib.check(lib.psgla_img_noise(shape, 42, 5, 11, z.data_ptr(), None), "noise")
+        x = torch.zeros(B, 3, H, W, device="cuda")
+        m = torch.zeros(1, 3, H, W, device="cuda")
+        pre = P._lib.PreParams()
+        pre.alg, pre.gain_data, pre.noise_scale, pre.seed, pre.chain_id0, pre.iteration = 0, 0.0, 1.0, 42, 5, 11
+        base = torch.empty_like(x)
+        den_in = torch.empty((B, H, W, 16), device="cuda", dtype=torch.bfloat16)
+        P._lib.check(lib.psgla_img_pre_inpaint(pre, shape, x.data_ptr(), m.data_ptr(), 1, m.data_ptr(), 1, None, base.data_ptr(),
+                                               den_in.data_ptr(), None), "pre")
+        torch.cuda.synchronize()
+        assert torch.equal(base, z)
+        zz = z.double().cpu().numpy().reshape(-1)
+        assert abs(zz.mean()) < 0.03 and abs(zz.var() - 1) < 0.05
+    # chains are independent streams
+    assert abs(np.corrcoef(z[0].cpu().numpy().reshape(-1), z[1].cpu().numpy().reshape(-1))[0, 1]) < 0.05
+
+
+def _psgla_kw(prm, n_iter, n_inter, n_mm, alpha=1.0):
+    return dict(alpha=torch.tensor(alpha, device="cuda"), lambd=torch.tensor(prm["lambd"], device="cuda"), sig_float=prm["s"],
+                delta=prm["delta"], n_iter=n_iter, n_inter=n_inter, n_inter_mmse=n_mm, seed=0)
+
+
+@pytest.mark.parametrize("problem", ["inpainting", "deblurring"])
+def test_psgla_replay_against_oracle(nets, problem):
+    den, net = nets
+    torch.manual_seed(0)
+    im = torch.rand(1, 3, 64, 64, device="cuda")
+    if problem == "inpainting":
+        dg, init, y, mask = P.make_inpainting(im)
+    else:
+        dg, init, y = P.make_deblurring(im, l=4, blur_type="uniform")
+    prm = io_.resolve_params("psgla")
+    n_iter, n_inter, n_mm = 50, 5, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    kw = _psgla_kw(prm, n_iter, n_inter, n_mm, alpha=0.8)
+    Xr, Mr, M2r = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw)
+    Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
+    assert len(Xg) == len(Xr) == 10 and len(Mg) == len(Mr) == n_iter // (n_mm + 1) and len(M2g) == len(M2r)
+    assert Xg[0].shape == Xr[0].shape == (3, 64, 64)
+    for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
+        assert (a - b).abs().max().item() < 2e-2
+    # rng="torch" reproduces the reference's own generator stream on this device
+    Xt, _, _ = P.psgla(init, dg, den, rng="torch", **kw)
+    assert all(torch.equal(a, b) for a, b in zip(Xt, Xg))
+
+
+def test_pnpula_replay_against_oracle(nets):
+    den, net = nets
+    torch.manual_seed(1)
+    im = torch.rand(1, 3, 48, 80, device="cuda")
+    dg, init, y = P.make_deblurring(im, l=4, blur_type="uniform")
+    prm = io_.resolve_params("pnp_ula", s=5.0)
+    n_iter, n_inter, n_mm = 30, 4, 5
+    g = torch.Generator(device="cuda").manual_seed(2)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    delta = torch.tensor(prm["delta"], dtype=torch.float32, device="cuda")
+    lambd = torch.tensor(prm["lambd"], dtype=torch.float32, device="cuda")
+    pg_ref = io_.make_prior_grad(net, 1.0, prm["s1"], prm["s2"], device="cuda")
+    Xr, Mr, M2r = io_.pnpula(init, dg, pg_ref, delta, lambd, n_iter=n_iter, n_inter=n_inter, n_inter_mmse=n_mm, device="cuda", noise=noise)
+    Xg, Mg, M2g = P.pnp_ula(init, dg, P.PriorGrad(den, 1.0, prm["s1"], prm["s2"]), delta, lambd, n_iter=n_iter, n_inter=n_inter,
+                            n_inter_mmse=n_mm, seed=2, noise=noise)
+    assert len(Xg) == len(Xr) and len(Mg) == len(Mr)
+    for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
+        assert (a - b).abs().max().item() < 2e-2
+
+
+def test_golden_fixture_sampler_bookkeeping(nets):
+    """The committed reference run (tests/golden, 16x16): same thinning / window counts and the same observation."""
+    den, _ = nets
+    im = torch.from_numpy(G["im"]).cuda()
+    dg, init, y, mask = P.make_inpainting(im)  # CUDA generator stream differs from the CPU fixture: compare structure only
+    alpha, lambd, s, delta, n_iter, n_inter, n_mm = G["psgla.params"]
+    Xg, Mg, M2g = P.psgla(init, dg, den, float(alpha), float(lambd), float(s), float(delta), n_iter=int(n_iter), n_inter=int(n_inter),
+                          n_inter_mmse=int(n_mm), seed=0)
+    assert len(Xg) == G["psgla.X"].shape[0] and len(Mg) == G["psgla.M"].shape[0] and len(M2g) == G["psgla.M2"].shape[0]
+    assert tuple(Xg[0].shape) == G["psgla.X"].shape[1:]
+    # with the fixture's own mask / observation / noise the data term is the reference's: check the first pre step
+    dgf = P.InpaintingDataGrad(torch.from_numpy(G["inp.mask"]).cuda(), torch.from_numpy(G["inp.y"]).cuda(), (1 / 255) ** 2)
+    x0 = torch.from_numpy(G["inp.init"]).cuda()
+    z0 = torch.from_numpy(G["psgla.noise"][0]).cuda()
+    want = x0 + (float(delta) / float(lambd)) * dgf(x0) + float(np.sqrt(2) * s) * z0
+    run = P.restoration_algorithms._Run(x0, dgf, den, 1, 1, 1, 0, torch.from_numpy(G["psgla.noise"][:1]).cuda(), "philox", None, 0)
+    pre = P._lib.PreParams()
+    pre.alg, pre.gain_data, pre.noise_scale = 0, (float(delta) / float(lambd)) / dgf.sigma2, float(np.sqrt(2) * s)
+    run.pre(0, pre)
+    assert (run.base - want).abs().max().item() < 1e-5
+
+
+def test_batched_chains_and_philox_mode(nets):
+    den, net = nets
+    torch.manual_seed(0)
+    im = torch.rand(1, 3, 32, 64, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im)
+    prm = io_.resolve_params("psgla")
+    kw = _psgla_kw(prm, 12, 3, 3)
+    Xb, Mb, _ = P.psgla(init, dg, den, n_chains=4, **kw)
+    assert Xb[0].shape == (4, 3, 32, 64) and len(Xb) == 4 and len(Mb) == 3
+    assert not torch.equal(Xb[-1][0], Xb[-1][1])  # independent noise per chain
+    # chain c of a batch == a single-chain run with chain_id0 = c (sharding invariance)
+    X1, _, _ = P.psgla(init, dg, den, n_chains=1, chain_id0=2, **kw)
+    assert (X1[-1][0] - Xb[-1][2]).abs().max().item() < 1e-6
+    # replay of the library's own Philox stream through the fp32 oracle
+    lib = P._lib.lib()
+    zs = []
+    for i in range(12):
+        z = torch.empty(1, 3, 32, 64, device="cuda")
+        P._lib.check(lib.psgla_img_noise(P._lib.ImgShape(1, 3, 32, 64), 0, 2, i, z.data_ptr(), None), "noise")
+        zs.append(z)
+    Xr, _, _ = io_.psgla(init, dg, net, device="cuda", noise=torch.stack(zs), **kw)
+    assert (Xr[-1] - X1[-1][0]).abs().max().item() < 2e-2
+
+
+def test_argument_errors(nets):
+    den, _ = nets
+    im = torch.rand(1, 3, 16, 16, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im)
+    with pytest.raises(ValueError, match="seed=None"):
+        P.psgla(init, dg, den, 1.0, 5.0, n_iter=10)
+    with pytest.raises(TypeError):
+        P.psgla(init, lambda x: x, den, 1.0, 5.0, n_iter=10, seed=0)
+    with pytest.raises(ZeroDivisionError):
+        P.psgla(init, dg, den, 1.0, 5.0, n_iter=5, n_inter=1, seed=0, save_images_online=True)
