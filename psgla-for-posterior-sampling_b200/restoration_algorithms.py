@@ -158,7 +158,7 @@ def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5,
     for i in range(run.n_iter):
         run.pre(i, pre)
         run.post(i, alpha_f)  # (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
-        if i % K == 0 and save_images_online:  # ZeroDivisionError for n_iter < 10, as in the reference (:246)
+        if save_images_online and i % K == 0:  # ZeroDivisionError for n_iter < 10 with the flag, as in the reference (:246)
             _save_online(path, name, i, run, {"lambda": lambd, "delta": delta})
     return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
 
@@ -184,7 +184,7 @@ def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000,
     for i in range(run.n_iter):
         run.pre(i, pre)
         run.post(i, gain)
-        if i % K == 0 and save_images_online:
+        if save_images_online and i % K == 0:
             _save_online(path, name, i, run, {"c_min": c_min, "c_max": c_max, "lambda": lambd, "delta": delta})
     return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
 
