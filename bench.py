@@ -1,0 +1,574 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the PSGLA / PnP-ULA hot path on B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Headline (BASELINE.json configs[1]): 2D Gaussian-mixture posterior sampling, the 18 cells
+(3 priors x 3 observations x {PSGLA, PnP-ULA}), 10^6 chains x 10^4 Langevin steps per cell and per GPU.
+A "step" of this bench is ONE cell = 10^10 chain-steps per GPU, one launch of the persistent chain kernel;
+the K timed steps cycle through the cells.  Chains shard over GPUs with no per-step communication (weak scaling:
+10^6 chains per GPU, global chain ids keep every chain's Philox stream independent of the GPU count).
+
+The same JSON line carries, under "image", the second half of BASELINE.json's metric: PSGLA image
+iterations/s at 256x256 with the DnCNN denoiser (configs[2]: random inpainting 50 %, sigma = 1/255, s = 2/255,
+lambda = 5, delta = s^2, alpha = 1), a batch of independent chains per GPU; there a "step" is one PSGLA iteration
+of the whole batch (1 fused Langevin kernel + 20 tcgen05 conv launches).
+
+Timing: CUDA events on the launching stream around every step, an L2 flush (256 MiB memset, not timed) between
+steps, W warm-up steps, barrier + synchronize on both sides, max over ranks.  `value` has its inputs resident in
+HBM; `e2e` goes through the public Python API with pinned-host inputs and outputs (copies inside the timed region).
+`--impl reference` times the reference's own CPU algorithm (the unmodified reference when /root/reference exists,
+else the oracle port) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PRIORS = ("symetric_gaussians", "cross", "disymmetric_gaussians")  # utils_2D.py:23-33
+OBSERVATIONS = ((0.0, 0.0), (0.0, -2.0), (-6.0, 6.0))  # sampling_2D.py:91
+GMM_ALGS = {  # sampling_2D.py:83-90,130-131
+    "psgla": dict(delta=0.3, alpha=2.0 / 3.0, epsilon=1.0),
+    "pnp_ula": dict(delta=0.1, alpha=1.5, epsilon=0.5),
+}
+CELLS = [(p, y, a) for a in ("psgla", "pnp_ula") for p in PRIORS for y in OBSERVATIONS]
+# algorithmic FP32 flop per chain-step (r = 2, FMA = 2 flop, constants folded on the host)
+FLOP_PER_CHAIN_STEP = {"psgla": 82, "pnp_ula": 88}
+MUFU_PER_CHAIN_STEP = 7
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.5; no measured FP32 figure in MEASURED_PEAKS.json
+DNCNN_FLOP_PER_PIXEL = 2 * 9 * (3 * 64 + 18 * 64 * 64 + 64 * 3)  # 1 334 016
+CONV64_FLOP_PER_PIXEL = 2 * 9 * 64 * 64  # 73 728, one hidden layer
+IMG_BYTES_PER_PIXEL_CHANNEL = 32  # X r/w, y, mask, E[X], E[X^2] r/w (fp32, Philox mode)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception as exc:  # noqa: BLE001 -- clocks are evidence, not a dependency
+            log("clock sampler unavailable:", exc)
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class Timer:
+    """Per-step CUDA events on the current stream; the L2 flush between steps is outside the event pairs."""
+
+    def __init__(self, torch, dev):
+        self.torch = torch
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.pairs = []
+
+    def flush(self):
+        self.flush_buf.zero_()
+
+    def step(self, fn):
+        self.flush()
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.pairs.append((e0, e1))
+
+    def total_ms(self):
+        self.torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in self.pairs]
+        self.pairs = []
+        return sum(ms), ms
+
+
+def barrier(torch, dist_mod):
+    torch.cuda.synchronize()
+    if dist_mod.world()[1] > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------ 2D GMM (product)
+def bench_gmm2d(args, P, torch, rank, ws, dev):
+    import numpy as np
+    n_chains, n_steps = args.chains, args.chain_steps
+    K, W = args.steps, args.warmup
+    chain_id0 = rank * n_chains
+    used = sorted({k % len(CELLS) for k in range(W + K)})
+    pops, x0s = {}, {}
+    for ci in used:
+        prior, y, alg = CELLS[ci]
+        mu, Sig, pi = P.gaussian_mixt_example(prior)
+        D = P.Theorical_MMSE(mu, Sig, pi)
+        prm = GMM_ALGS[alg]
+        x0 = torch.tensor(y, dtype=torch.float32, device=dev).repeat(n_chains, 1).contiguous()
+        pops[ci] = P.GMMChains(alg, np.array(y), prm["delta"], np.eye(2), 1.0, D, prm["alpha"], prm["epsilon"],
+                               n_chains=n_chains, x0=x0, seed=args.seed, chain_id0=chain_id0, dtype="float32", device=dev)
+        x0s[ci] = x0
+
+    def one(k):
+        ch = pops[k % len(CELLS)]
+        ch.state.copy_(x0s[k % len(CELLS)])
+        ch.step = 0
+        return ch
+
+    for k in range(W):
+        one(k).run(n_steps)
+    timer = Timer(torch, dev)
+    barrier(torch, P.dist)
+    flop = 0.0
+    for k in range(W, W + K):
+        ch = one(k)
+        timer.step(lambda: ch.run(n_steps))
+        flop += FLOP_PER_CHAIN_STEP[CELLS[k % len(CELLS)][2]] * float(n_chains) * n_steps
+    total_ms, per_step = timer.total_ms()
+    barrier(torch, P.dist)
+    total_ms = P.dist.max_over_ranks(total_ms, dev)
+
+    # ---- e2e: the public API with pinned-host initial states and pinned-host results, copies inside the timed region
+    x0_host = {ci: torch.tensor(CELLS[ci][1], dtype=torch.float32).repeat(n_chains, 1).pin_memory() for ci in used}
+    out_host = torch.empty((n_chains, 2), dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        ci = k % len(CELLS)
+        prior, y, alg = CELLS[ci]
+        prm = GMM_ALGS[alg]
+        mu, Sig, pi = P.gaussian_mixt_example(prior)
+        ch = P.GMMChains(alg, np.array(y), prm["delta"], np.eye(2), 1.0, P.Theorical_MMSE(mu, Sig, pi), prm["alpha"],
+                         prm["epsilon"], n_chains=n_chains, x0=x0_host[ci], seed=args.seed, chain_id0=chain_id0,
+                         dtype="float32", device=dev)
+        ch.run(n_steps)
+        out_host.copy_(ch.state, non_blocking=True)
+
+    for k in range(min(W, 3)):
+        e2e_step(k)
+    barrier(torch, P.dist)
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier(torch, P.dist)
+    e2e_ms = P.dist.max_over_ranks(e2e_ms, dev)
+
+    # ---- quality next to the speed: W2^2 to the true posterior per cell (utils_2D.py:235-244), all ranks' chains
+    w2 = {}
+    for ci in used:
+        prior, y, alg = CELLS[ci]
+        finals = P.dist.gather_to_rank0(pops[ci].state)
+        if rank == 0:
+            mu, Sig, pi = P.gaussian_mixt_example(prior)
+            rng = np.random.default_rng(1234)
+            ref = P.sample_posterior(np.eye(2), np.array(y), 1.0, 10000, mu, Sig, pi, rng=rng)
+            sub = finals[torch.randperm(finals.shape[0], device=finals.device)[:10000]].double().cpu().numpy()
+            w2["%s|%s|y=(%g,%g)" % (alg, prior, y[0], y[1])] = round(P.Wasserstein_distance(sub, ref, rng=rng), 4)
+    units = float(n_chains) * n_steps * K * ws
+    return dict(value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
+                e2e_value=units / (e2e_ms * 1e-3), e2e_ms=e2e_ms, h2d=n_chains * 2 * 4, d2h=n_chains * 2 * 4, w2=w2)
+
+
+# ------------------------------------------------------------------------------------------------ image PSGLA (product)
+def synthetic_image(torch, H, W, seed, dev):
+    """Smooth synthetic colour image in [0,1] (no dataset travels to the GPU box)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand((1, 3, H // 16 + 2, W // 16 + 2), generator=g)
+    im = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0, 1)
+    return im.to(dev).contiguous()
+
+
+def bench_image(args, P, torch, rank, ws, dev, peaks):
+    from importlib import import_module
+    _lib = import_module("psgla_b200._lib")
+    B, H, Wd = args.image_chains, args.image_size, args.image_size
+    K, W = args.image_steps, max(args.warmup, 3)
+    s = 2.0 / 255.0  # sampling_images.py:170-198: DnCNN => s = 2/255, lambda = 5, delta = s^2
+    kw = dict(alpha=1.0, lambd=5.0, sig_float=s, delta=s * s, n_inter=10, n_inter_mmse=10, seed=args.seed)
+    im = synthetic_image(torch, H, Wd, 0, dev)
+    den = P.DnCNN(pretrained=P.lipschitz_dncnn_state_dict(0), device=dev)
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    run = P.psgla_run(init, dg, den, n_iter=W + K, n_chains=B, chain_id0=rank * B, **kw)
+    for i in range(W):
+        run.step(i)
+    timer = Timer(torch, dev)
+    barrier(torch, P.dist)
+    for i in range(W, W + K):
+        timer.step(lambda: run.step(i))
+    total_ms, per_step = timer.total_ms()
+    barrier(torch, P.dist)
+    total_ms = P.dist.max_over_ranks(total_ms, dev)
+    finite = bool(torch.isfinite(run.X).all().item())
+    x_absmax = float(run.X.abs().max().item())
+
+    # ---- the dominant kernel alone: the 18 hidden 64->64 conv layers, CUDA events around back-to-back launches
+    shape = _lib.ImgShape(B, 3, H, Wd)
+    wsbuf, _ = den.buffers(shape)
+    half = (B * H * Wd * 64 * 2 + 1023) // 1024 * 1024
+    bufs = [wsbuf.data_ptr(), wsbuf.data_ptr() + half]
+    lib = _lib.lib()
+    st = _lib.stream_ptr(dev)
+
+    def hidden_layers():
+        for l in range(1, 19):
+            rc = lib.psgla_conv3x3_layer(den.packed.data_ptr(), den.depth, l, shape, bufs[l & 1], bufs[(l + 1) & 1], 1, st)
+            if rc:
+                _lib.check(rc, "psgla_conv3x3_layer")
+
+    hidden_layers()
+    reps = 5
+    for _ in range(reps):
+        timer.step(hidden_layers)
+    conv_ms, _ = timer.total_ms()
+    conv_launch_ms = conv_ms / (reps * 18)
+
+    # ---- the fused Langevin "pre" kernel alone (HBM-bound stage)
+    def pre_only():
+        run.pre(W + K - 1, run.pre_params)
+    pre_only()
+    for _ in range(reps):
+        timer.step(pre_only)
+    pre_ms, _ = timer.total_ms()
+    pre_launch_ms = pre_ms / reps
+
+    # ---- e2e: psgla() itself, pinned-host image / mask / observation in, pinned-host posterior mean out
+    n_e2e = max(K, 11)
+    host = dict(init=init.cpu().pin_memory(), mask=mask.cpu().pin_memory(), y=y.cpu().pin_memory())
+    out_host = torch.empty((B, 3, H, Wd), dtype=torch.float32).pin_memory()
+
+    def e2e_call():
+        with contextlib.redirect_stdout(sys.stderr):
+            dg2 = P.InpaintingDataGrad(host["mask"].to(dev, non_blocking=True), host["y"].to(dev, non_blocking=True),
+                                       dg.sigma2)
+            Xl, Mm, _ = P.psgla(host["init"].to(dev, non_blocking=True), dg2, den, n_iter=n_e2e, n_chains=B,
+                                chain_id0=rank * B, **kw)
+            out_host.copy_(Mm[-1], non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_call()
+    barrier(torch, P.dist)
+    t0 = time.perf_counter()
+    e2e_call()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier(torch, P.dist)
+    e2e_ms = P.dist.max_over_ranks(e2e_ms, dev)
+
+    px = B * H * Wd
+    conv_tflops = CONV64_FLOP_PER_PIXEL * px / (conv_launch_ms * 1e-3) / 1e12
+    step_tflops = DNCNN_FLOP_PER_PIXEL * px * K / (total_ms * 1e-3) / 1e12
+    pre_gbs = (IMG_BYTES_PER_PIXEL_CHANNEL - 16) * 3 * px / (pre_launch_ms * 1e-3) / 1e9  # pre touches X, y, mask, base
+    return {
+        "metric": "psgla_image_iterations_per_sec_256x256_dncnn", "unit": "image-iterations/s",
+        "value": B * K * ws / (total_ms * 1e-3), "ms_per_step": total_ms / K, "steps": K, "warmup": W,
+        "config": {"workload": "random inpainting 50%%, sigma=1/255, PSGLA s=2/255 lambda=5 delta=s^2 alpha=1, DnCNN depth 20 "
+                               "(seeded random-init, Lipschitz 0.9), %d chains/GPU of %dx%dx3, in-kernel Philox" % (B, H, Wd),
+                   "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
+        "dtype": "bf16 activations / fp32 accumulate, fp32 state",
+        "gpu_launches": 21 * K,
+        "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
+                "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
+        "roofline": {"kernel": "conv3x3_kernel<64,64,EPI_HIDDEN> (18 of the 21 launches per iteration)", "bound": "tensor",
+                     "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
+                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms, "traffic": None},
+        "whole_iteration_tensor_tflops": step_tflops,
+        "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
+        "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": pre_gbs / peaks["hbm_gbs"], "launch_ms": pre_launch_ms},
+        "state_finite": finite, "state_absmax": x_absmax,
+    }
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+def _cpu_chain_worker(job):
+    """One host core: the reference's single-chain Python loop (sampling_2D.py:48-72 / :21-45)."""
+    alg, prior, y, n, seed, use_ref = job
+    import numpy as np
+    from oracle import gmm2d_oracle as o
+    fn = None
+    if use_ref:
+        from oracle import ref_loader
+        ns = ref_loader.load_sampling_2D()
+        u2 = ref_loader.load_utils_2D()
+        mu, Sig, pi = u2.gaussian_mixt_example(prior)
+        D = u2.Theorical_MMSE(mu, Sig, pi)
+        np.random.seed(seed)
+        prm = GMM_ALGS[alg]
+        t0 = time.perf_counter()
+        if alg == "psgla":
+            ns.SnoPnP_ULA(n + 1, np.array(y), np.array(y), prm["delta"], np.eye(2), 1, D, prm["alpha"])
+        else:
+            ns.PnP_ULA(n + 1, np.array(y), np.array(y), prm["delta"], np.eye(2), 1, D, prm["epsilon"], prm["alpha"])
+        return time.perf_counter() - t0
+    mu, Sig, pi = o.gaussian_mixt_example(prior)
+    D = o.theorical_mmse(mu, Sig, pi)
+    prm = GMM_ALGS[alg]
+    noise = np.random.default_rng(seed).standard_normal((n, 2))
+    t0 = time.perf_counter()
+    if alg == "psgla":
+        fn = o.snopnp_ula(n + 1, np.array(y), np.array(y), prm["delta"], np.eye(2), 1, D, prm["alpha"], noise=noise)
+    else:
+        fn = o.pnp_ula(n + 1, np.array(y), np.array(y), prm["delta"], np.eye(2), 1, D, prm["epsilon"], prm["alpha"], noise=noise)
+    assert fn.shape == (n + 1, 2)
+    return time.perf_counter() - t0
+
+
+def _reference_available():
+    from oracle import ref_loader
+    return ref_loader.reference_available()
+
+
+def cpu_baseline_gmm2d(n_steps):
+    use_ref = _reference_available()
+    dt = _cpu_chain_worker(("psgla", "symetric_gaussians", (0.0, -2.0), n_steps, 0, use_ref))
+    return {"value": n_steps / dt, "unit": "chain-steps/s", "cores": 1, "kind": "reference" if use_ref else "port",
+            "sample": "1 chain x %d PSGLA steps, symetric_gaussians prior, y=(0,-2), float64 Python loop "
+                      "(the reference is single-threaded; independent chains scale with cores)" % n_steps}
+
+
+def cpu_baseline_image(args, n_iter=12):
+    """The reference's psgla loop on the host cores with the fp32 torch DnCNN of the oracle (same weights, same problem)."""
+    import torch
+    import psgla_b200 as P
+    from oracle import image_oracle as io_
+    H = args.image_size
+    im = synthetic_image(torch, H, H, 0, "cpu")
+    net = io_.DnCNN()
+    net.load_state_dict(P.lipschitz_dncnn_state_dict(0))
+    net.eval()
+    prob = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0, device="cpu")
+    s = 2.0 / 255.0
+    kw = dict(alpha=torch.tensor(1.0), lambd=torch.tensor(5.0), sig_float=s, delta=s * s, n_inter=10, n_inter_mmse=10, seed=0)
+    fn, kind = io_.psgla, "port"
+    if _reference_available():
+        from oracle import ref_loader
+        ra = ref_loader.load_restoration_algorithms()
+        fn, kind = (lambda *a, **k: ra.psgla(*a, device="cpu", **k)), "reference"
+    else:
+        fn = lambda *a, **k: io_.psgla(*a, device="cpu", **k)  # noqa: E731
+    with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")):
+        fn(prob["init"], prob["data_grad"], net, n_iter=10, **kw)  # warm-up (n_iter >= 10: restoration_algorithms.py:246)
+        t0 = time.perf_counter()
+        fn(prob["init"], prob["data_grad"], net, n_iter=n_iter, **kw)
+        dt = time.perf_counter() - t0
+    return {"value": n_iter / dt, "unit": "image-iterations/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d PSGLA iterations, 1 chain, %dx%dx3, fp32 torch DnCNN on the host" % (n_iter, H, H)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the headline workload on every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    use_ref = _reference_available()
+    n = args.ref_chain_steps
+    K, W = args.steps, args.warmup
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for k in range(W + K):
+            prior, y, alg = CELLS[k % len(CELLS)]
+            jobs = [(alg, prior, y, n, 1000 * k + c, use_ref) for c in range(cores)]
+            dt = max(pool.map(_cpu_chain_worker, jobs))  # slowest core's loop time; process start-up is not counted
+            if k >= W:
+                times.append(dt)
+    total = sum(times)
+    value = cores * n * K / total
+    kind = "reference" if use_ref else "port"
+    sample = "%d independent chains (one per host core) x %d steps per bench step, cells cycled as in the GPU arm" % (cores, n)
+    line = {
+        "impl": "reference", "metric": "langevin_chain_steps_per_sec_2d_gmm", "value": value, "unit": "chain-steps/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": total / K * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_block(args),
+        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not args.skip_image:
+        try:
+            line["image"] = {"impl": "reference", "metric": "psgla_image_iterations_per_sec_256x256_dncnn",
+                             **cpu_baseline_image(args, n_iter=12)}
+        except Exception as exc:  # noqa: BLE001
+            line["image"] = {"impl": "reference", "error": repr(exc)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+def config_block(args):
+    return {"workload": "2D GMM posterior sampling, 18 cells = 3 priors x 3 observations x {PSGLA, PnP-ULA} "
+                        "(sampling_2D.py:83-91,130-131), %d chains x %d steps per cell per GPU, one cell per bench step"
+                        % (args.chains, args.chain_steps),
+            "chains_per_gpu": args.chains, "steps_per_chain": args.chain_steps, "cells": len(CELLS),
+            "rng": "in-kernel Philox4x32-10 + Box-Muller, subsequence = global chain id",
+            "sharding": "chains split over GPUs, no per-step communication; NCCL gather of finals for W2",
+            "l2": "256 MiB flush between timed steps (state lives in registers; HBM sees 16 B per chain per step of the bench)"}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=18)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=1000000, help="2D chains per GPU")
+    ap.add_argument("--chain-steps", type=int, default=10000, help="Langevin steps per chain per cell")
+    ap.add_argument("--image-chains", type=int, default=32, help="independent PSGLA chains per GPU")
+    ap.add_argument("--image-size", type=int, default=256)
+    ap.add_argument("--image-steps", type=int, default=20)
+    ap.add_argument("--ref-chain-steps", type=int, default=20000, help="--impl reference: steps per core per bench step")
+    ap.add_argument("--cpu-sample-steps", type=int, default=100000, help="cpu_baseline sample: steps of one CPU chain")
+    ap.add_argument("--skip-image", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import psgla_b200 as P
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    rank, ws, local = P.dist.init_from_env("nccl")
+    if ws != max(args.gpus, 1):
+        log("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, ws))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    arch = P._lib.lib().psgla_device_arch()
+    if arch < 100:
+        raise SystemExit("libpsgla_b200 targets sm_100a; device reports sm_%d" % arch)
+    peaks = measured_peaks()
+    W = max(args.warmup, 3)
+    if W != args.warmup:
+        log("warm-up raised to 3 steps (timing rule)")
+        args.warmup = W
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    g = bench_gmm2d(args, P, torch, rank, ws, dev)
+    img = None
+    if not args.skip_image:
+        img = bench_image(args, P, torch, rank, ws, dev, peaks)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if ws > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    K = args.steps
+    achieved_tflops = g["flop"] * ws / (g["total_ms"] * 1e-3) / 1e12
+    line = {
+        "metric": "langevin_chain_steps_per_sec_2d_gmm", "value": g["value"], "unit": "chain-steps/s", "n_gpus": ws,
+        "steps": K, "warmup": args.warmup, "ms_per_step": g["total_ms"] / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args),
+        "clocks": clocks,
+        "e2e": {"value": g["e2e_value"], "unit": "chain-steps/s", "h2d_bytes_per_step": g["h2d"],
+                "d2h_bytes_per_step": g["d2h"]},
+        "gpu_launches": K,
+        "roofline": {"kernel": "gmm2d_kernel<float,*,true,4> (one launch per step)", "bound": "fp32",
+                     "achieved": achieved_tflops / ws, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / ws / FP32_PEAK_TFLOPS_NOMINAL,
+                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure); "
+                                    "algorithmic 82/88 flop + 7 MUFU per chain-step, Philox INT work not counted",
+                     "mufu_gops": g["value"] / ws * MUFU_PER_CHAIN_STEP / 1e9,
+                     "launch_ms": g["total_ms"] / K, "traffic": None},
+        "w2_squared_to_true_posterior": g["w2"],
+    }
+    if img is not None:
+        line["image"] = img
+    if ws == 1 and not args.skip_cpu:
+        line["cpu_baseline"] = cpu_baseline_gmm2d(args.cpu_sample_steps)
+        if img is not None:
+            try:
+                img["cpu_baseline"] = cpu_baseline_image(args)
+            except Exception as exc:  # noqa: BLE001
+                img["cpu_baseline"] = {"error": repr(exc)[:200]}
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["DnCNN", "random_dncnn_state_dict"]
+__all__ = ["DnCNN", "random_dncnn_state_dict", "lipschitz_dncnn_state_dict"]
 
 
 def random_dncnn_state_dict(seed=0, depth=20, nf=64, scale=1.0):
@@ -32,6 +32,34 @@ def random_dncnn_state_dict(seed=0, depth=20, nf=64, scale=1.0):
     for i in range(depth - 2):
         conv("conv_list.%d" % i, nf, nf)
     conv("out_conv", 3, nf)
+    return sd
+
+
+def _conv_operator_norm(w, spatial=16, n_power_iter=40):
+    """Spectral norm of the circular 3x3 convolution with weight ``w`` [O,I,3,3] on a spatial x spatial grid: the
+    operator is block-diagonalised by the 2-D DFT, so the norm is the largest singular value over frequencies."""
+    k = torch.zeros((w.shape[0], w.shape[1], spatial, spatial), dtype=torch.float64)
+    k[:, :, :3, :3] = w.double()
+    kf = torch.fft.fft2(k).permute(2, 3, 0, 1).reshape(-1, w.shape[0], w.shape[1])
+    gram = kf.conj().transpose(1, 2) @ kf  # per-frequency Hermitian [I, I]
+    v = torch.ones((gram.shape[0], gram.shape[1], 1), dtype=gram.dtype)
+    lam = torch.ones(gram.shape[0], dtype=torch.float64)
+    for _ in range(n_power_iter):  # batched power iteration; a norm estimate from below, within 1e-3 after 40 rounds
+        v = gram @ v
+        lam = torch.linalg.vector_norm(v, dim=(1, 2))
+        v = v / lam.clamp_min(1e-300)[:, None, None]
+    return float(lam.max().sqrt())
+
+
+def lipschitz_dncnn_state_dict(seed=0, depth=20, nf=64, lipschitz=0.9, spatial=16):
+    """Seeded random-init DnCNN whose residual branch has Lipschitz bound ``lipschitz`` < 1 (the stand-in BASELINE.json
+    prescribes for the unavailable ``dncnn_sigma2_lipschitz_color.pth``, README.md:28-29): every conv is divided by
+    its exact circular operator norm and the layers share the bound evenly.  Set-up code, runs once on the CPU."""
+    sd = random_dncnn_state_dict(seed, depth, nf)
+    per_layer = lipschitz ** (1.0 / depth)
+    for name in ["in_conv"] + ["conv_list.%d" % i for i in range(depth - 2)] + ["out_conv"]:
+        w = sd[name + ".weight"]
+        sd[name + ".weight"] = (w * (per_layer / _conv_operator_norm(w, spatial))).float()
     return sd
 
 

@@ -27,7 +27,7 @@ from . import _lib
 from .denoisers import DnCNN
 from .operators import DeblurDataGrad, InpaintingDataGrad, PriorGrad
 
-__all__ = ["psgla", "pnpula", "pnp_ula"]
+__all__ = ["psgla", "pnpula", "pnp_ula", "psgla_run", "pnpula_run"]
 
 
 def _f(v):
@@ -89,6 +89,14 @@ class _Run:
             self.y = data_grad.y.to(self.device).expand(-1, 3, -1, -1).contiguous()
             self.mask = data_grad.mask.to(self.device).expand(-1, 3, -1, -1).contiguous()
 
+    def configure(self, pre, gain):
+        self.pre_params, self.gain = pre, float(gain)
+
+    def step(self, i):
+        """Iteration i of the sampler: fused Langevin "pre" kernel, then DnCNN + fused "post" epilogue."""
+        self.pre(i, self.pre_params)
+        self.post(i, self.gain)
+
     def _out(self, t):
         return t[0] if self.squeeze else t
 
@@ -139,28 +147,53 @@ def _save_online(path, name, i, run, extra):
     torch.save(d, (path or "") + "/" + (name or "") + "_sampling.pth")
 
 
+def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
+              n_inter_mmse=1000, seed=None, *, noise=None, rng="philox", n_chains=None, chain_id0=0):
+    """The stepping object behind ``psgla``: ``run.step(i)`` issues iteration i (one "pre" launch + the DnCNN layer
+    chain); ``run.Xlist`` / ``run.Xlist_mmse`` / ``run.Xlist_mmse2`` are the reference's three lists."""
+    run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    delta32 = float(np.float32(delta))
+    sig32 = float(np.float32(sig_float))
+    pre = _lib.PreParams()
+    pre.alg = _lib.ALG_PSGLA
+    pre.gain_data = (delta32 / _f(lambd)) / run.dg.sigma2
+    pre.noise_scale = float(np.float32(np.float32(np.sqrt(2)) * np.float32(sig32)))
+    pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0
+    run.configure(pre, _f(alpha))  # (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
+    return run
+
+
 def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
           n_inter_mmse=1000, seed=None, device=None, path=None, save_images_online=False, name=None, *, noise=None,
           rng="philox", n_chains=None, chain_id0=0):
     """PSGLA (restoration_algorithms.py:163-285):  Y = X + (delta/lambd) data_grad(X) + sqrt(2) sig Z;
     X = (1 - alpha) Y + alpha D(Y).  Returns (Xlist, Xlist_mmse, Xlist_mmse2)."""
-    run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
-    alpha_f, lambd_f = _f(alpha), _f(lambd)
-    delta32 = float(np.float32(delta))
-    sig32 = float(np.float32(sig_float))
+    run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, n_inter, n_inter_mmse, seed,
+                    noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0)
     print("delta = {}, sigma = {}".format(delta, sig_float))
     K = int(run.n_iter / 10)
-    pre = _lib.PreParams()
-    pre.alg = _lib.ALG_PSGLA
-    pre.gain_data = (delta32 / lambd_f) / run.dg.sigma2
-    pre.noise_scale = float(np.float32(np.float32(np.sqrt(2)) * np.float32(sig32)))
-    pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0
     for i in range(run.n_iter):
-        run.pre(i, pre)
-        run.post(i, alpha_f)  # (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
+        run.step(i)
         if save_images_online and i % K == 0:  # ZeroDivisionError for n_iter < 10 with the flag, as in the reference (:246)
             _save_online(path, name, i, run, {"lambda": lambd, "delta": delta})
     return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
+
+
+def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
+               c_min=-1, c_max=2, *, noise=None, rng="philox", n_chains=None, chain_id0=0):
+    """The stepping object behind ``pnpula`` (see ``psgla_run``)."""
+    if not isinstance(prior_grad, PriorGrad):
+        raise TypeError("prior_grad must be a PriorGrad(denoiser, alpha, s1, s2) structured callable")
+    run = _Run(init, data_grad, prior_grad.denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    delta_f, lambd_f = _f(delta), _f(lambd)
+    pre = _lib.PreParams()
+    pre.alg = _lib.ALG_PNPULA
+    pre.gain_data = delta_f / run.dg.sigma2
+    pre.noise_scale = float(np.float32(math.sqrt(2 * delta_f)))
+    pre.proj_gain = delta_f / lambd_f
+    pre.c_min, pre.c_max = float(c_min), float(c_max)
+    run.configure(pre, delta_f * prior_grad.alpha / prior_grad.s2)
+    return run
 
 
 def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
@@ -168,22 +201,12 @@ def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000,
            n_chains=None, chain_id0=0):
     """PnP-ULA (restoration_algorithms.py:38-160):
     X+ = X + delta (prior_grad(X) - (X - proj_[c_min,c_max] X)/lambd + data_grad(X)) + sqrt(2 delta) Z."""
-    if not isinstance(prior_grad, PriorGrad):
-        raise TypeError("prior_grad must be a PriorGrad(denoiser, alpha, s1, s2) structured callable")
-    run = _Run(init, data_grad, prior_grad.denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
-    delta_f, lambd_f = _f(delta), _f(lambd)
+    run = pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter, n_inter, n_inter_mmse, seed, c_min, c_max,
+                     noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0)
     print("delta = {}".format(delta.float() if isinstance(delta, torch.Tensor) else delta))
     K = int(run.n_iter / 10)
-    pre = _lib.PreParams()
-    pre.alg = _lib.ALG_PNPULA
-    pre.gain_data = delta_f / run.dg.sigma2
-    pre.noise_scale = float(np.float32(math.sqrt(2 * delta_f)))
-    pre.proj_gain = delta_f / lambd_f
-    pre.c_min, pre.c_max = float(c_min), float(c_max)
-    gain = delta_f * prior_grad.alpha / prior_grad.s2
     for i in range(run.n_iter):
-        run.pre(i, pre)
-        run.post(i, gain)
+        run.step(i)
         if save_images_online and i % K == 0:
             _save_online(path, name, i, run, {"c_min": c_min, "c_max": c_max, "lambda": lambd, "delta": delta})
     return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2

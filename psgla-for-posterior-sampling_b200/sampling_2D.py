@@ -63,9 +63,16 @@ class GMMChains:
         self.tdtype = {"float32": torch.float32, "float64": torch.float64}[str(dtype).replace("torch.", "")]
         self.precision = 0 if self.tdtype == torch.float32 else 1
         self.n_chains = int(n_chains)
-        x0 = np.asarray(y if x0 is None else x0, dtype=np.float64)
-        x0 = np.broadcast_to(x0.reshape(-1, 2), (self.n_chains, 2))
-        self.state = torch.from_numpy(np.ascontiguousarray(x0)).to(self.device, self.tdtype).contiguous()
+        if isinstance(x0, torch.Tensor):  # (n_chains, 2) host (pinned: asynchronous copy) or device tensor
+            if tuple(x0.shape) != (self.n_chains, 2):
+                raise ValueError("a tensor x0 must have shape (n_chains, 2)")
+            self.state = x0.to(self.device, self.tdtype, non_blocking=True).contiguous()
+            if self.state.data_ptr() == x0.data_ptr():
+                self.state = self.state.clone()
+        else:
+            x0 = np.asarray(y if x0 is None else x0, dtype=np.float64)
+            x0 = np.broadcast_to(x0.reshape(-1, 2), (self.n_chains, 2))
+            self.state = torch.from_numpy(np.ascontiguousarray(x0)).to(self.device, self.tdtype).contiguous()
         self.seed, self.chain_id0, self.step = int(seed), int(chain_id0), 0
 
     def run(self, n_steps, noise=None, thin=0):

@@ -153,22 +153,35 @@ def test_sharding_and_segmentation_invariance():
     assert torch.equal(full, ch.state)
 
 
+@pytest.mark.parametrize("alg", ["psgla", "pnp_ula"])
 @pytest.mark.parametrize("name", o.PRIOR_NAMES)
-def test_statistical_parity_with_closed_form_posterior(name):
-    """PSGLA at the script's constants: component weights and means against utils_2D.py:139-162, and W2^2 to exact
-    posterior samples on 1000-point subsamples in the range the reference's figure reports (<= ~0.7)."""
+def test_statistical_parity_with_oracle_population(name, alg):
+    """In-kernel Philox chains against an oracle population driven by NumPy noise: the two empirical laws after 600
+    steps must agree (means within 6 standard errors, covariances within 10 %), and both must sit near the closed-form
+    posterior (utils_2D.py:139-162) up to the discretisation bias of the scheme (the reference's figure reports W2^2
+    up to ~0.8 for PSGLA and ~24 for PnP-ULA at these step sizes)."""
     mu, Sig, pi = P.gaussian_mixt_example(name)
     D = P.Theorical_MMSE(mu, Sig, pi)
     y = np.array([0.0, -2.0])
-    fin, _ = P.run_chains("psgla", 2000, y, 0.3, np.eye(2), 1, D, 2 / 3, n_chains=200000, seed=0)
+    prm = dict(psgla=dict(delta=0.3, alpha=2 / 3, epsilon=1.0), pnp_ula=dict(delta=0.1, alpha=1.5, epsilon=0.5))[alg]
+    n_steps, n_gpu, n_cpu = 600, 400000, 20000
+    fin, _ = P.run_chains(alg, n_steps, y, prm["delta"], np.eye(2), 1, D, prm["alpha"], prm["epsilon"], n_chains=n_gpu, seed=0)
     X = fin.double().cpu().numpy()
     assert np.all(np.isfinite(X))
+    Xo = o.run_chains(alg, n_steps, np.tile(y, (n_cpu, 1)), y, prm["delta"], np.eye(2), 1, mu, Sig, pi, prm["alpha"],
+                      epsilon=prm["epsilon"], rng=np.random.default_rng(11))
+    se = np.sqrt(Xo.var(0) / n_cpu + X.var(0) / n_gpu)
+    assert np.all(np.abs(X.mean(0) - Xo.mean(0)) < 6 * se + 1e-3), (X.mean(0), Xo.mean(0), se)
+    cg, co = np.cov(X.T), np.cov(Xo.T)
+    assert np.abs(cg - co).max() < 0.1 * np.abs(co).max() + 0.02, (cg, co)
+    # sliced W2 between the two populations is at the Monte-Carlo floor of two 20 000-point clouds of one law
+    assert P.sliced_wasserstein_distance(X[:n_cpu], Xo, seed=0) < 0.08
+    # and both sit as close to the exact posterior as the scheme's bias allows (W2^2 averaged over 6 subsamples)
     rng = np.random.default_rng(0)
     post = P.sample_posterior(np.eye(2), y, 1, 200000, mu, Sig, pi, rng=rng)
-    assert np.abs(X.mean(0) - post.mean(0)).max() < 0.25
-    w = P.Wasserstein_distance(X, post, rng=rng)
-    wref = P.Wasserstein_distance(post, P.sample_posterior(np.eye(2), y, 1, 200000, mu, Sig, pi, rng=rng), rng=rng)
-    assert w < max(1.0, 6 * wref), (w, wref)
+    w_gpu = np.mean([P.Wasserstein_distance(X, post, rng=rng) for _ in range(6)])
+    w_cpu = np.mean([P.Wasserstein_distance(Xo, post, rng=rng) for _ in range(6)])
+    assert abs(w_gpu - w_cpu) < 0.5 * max(w_cpu, 0.2) + 0.15, (w_gpu, w_cpu)
 
 
 def test_metric_each_step_interleaving():
