@@ -72,7 +72,7 @@ class GMMChains:
         else:
             x0 = np.asarray(y if x0 is None else x0, dtype=np.float64)
             x0 = np.broadcast_to(x0.reshape(-1, 2), (self.n_chains, 2))
-            self.state = torch.from_numpy(np.ascontiguousarray(x0)).to(self.device, self.tdtype).contiguous()
+            self.state = torch.from_numpy(np.array(x0, dtype=np.float64, order="C")).to(self.device, self.tdtype).contiguous()
         self.seed, self.chain_id0, self.step = int(seed), int(chain_id0), 0
 
     def run(self, n_steps, noise=None, thin=0):

@@ -196,7 +196,7 @@ def test_metric_each_step_interleaving():
 
 def test_bad_arguments_raise():
     D = P.Theorical_MMSE(*P.gaussian_mixt_example("cross"))
-    with pytest.raises(RuntimeError, match="delta"):
+    with pytest.raises(RuntimeError, match="must be > 0"):
         P.run_chains("psgla", 4, np.zeros(2), -1.0, np.eye(2), 1, D, 2 / 3)
     with pytest.raises(ValueError):
         P.Theorical_MMSE([np.zeros(2)] * 17, [np.eye(2)] * 17, [1 / 17] * 17)
