@@ -495,10 +495,13 @@ def main():
     ap.add_argument("--ref-chain-steps", type=int, default=20000, help="--impl reference: steps per core per bench step")
     ap.add_argument("--cpu-sample-steps", type=int, default=100000, help="cpu_baseline sample: steps of one CPU chain")
     ap.add_argument("--skip-image", action="store_true")
+    ap.add_argument("--only-image", action="store_true", help="profiling aid: shrink the 2D part to a token run")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.only_image:
+        args.chains, args.chain_steps, args.steps, args.skip_cpu = 4096, 16, 1, True
 
     if args.impl == "reference":
         run_reference(args)

@@ -19,8 +19,10 @@
 //   X+ = base + gain * (conv + bias), sample thinning and running E[X], E[X^2] (restoration_algorithms.py:238-262).
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -32,13 +34,16 @@ using namespace sm100;
 
 constexpr int TILE_M = 128;
 constexpr int BOX_W = TILE_M + 2;
-constexpr int NSTAGE = 8;
-constexpr int NACC = 2;
-constexpr int CONV_THREADS = 192;
+constexpr int NSTAGE = 6;     // input-row ring slots
+constexpr int NACC = 4;       // TMEM accumulator stages; stage s is drained by epilogue group s & 1
+constexpr int EPI_WARPS = 8;  // two groups of four warps (one warp per TMEM lane quarter)
+constexpr int CONV_THREADS = 64 + 32 * EPI_WARPS;
 
 constexpr int round_up_c(int v, int a) { return (v + a - 1) / a * a; }
 
-template <int CIN, int NOUT>
+enum { EPI_HIDDEN = 0, EPI_POST = 2 };
+
+template <int CIN, int NOUT, int EPI>
 struct ConvCfg {
   static constexpr int ROW_BYTES = CIN * 2;
   static constexpr int BOX_BYTES = BOX_W * ROW_BYTES;
@@ -49,11 +54,14 @@ struct ConvCfg {
   static constexpr int TAP_BYTES = NOUT * ROW_BYTES;
   static constexpr int W_BYTES = 9 * TAP_BYTES;
   static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
-  static constexpr int OFF_BIAS = OFF_RING + NSTAGE * SLOT_BYTES;
+  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? 32 * NOUT * 2 : 0;  // one 32-pixel output box per epilogue warp
+  static constexpr int OFF_STAGE = OFF_RING + NSTAGE * SLOT_BYTES;
+  static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 256;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the dynamic base to 1024
   static constexpr int TMEM_COLS = (NACC * NOUT) < 32 ? 32 : NACC * NOUT;
-  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
 struct ConvParams {
@@ -61,9 +69,7 @@ struct ConvParams {
   int R, strips, row_blocks, n_items;
   const uint8_t* weights;  // 9 taps, swizzled
   const float* bias;       // NOUT floats
-  __nv_bfloat16* out;      // EPI_HIDDEN
   int relu;
-  int desc_mode;  // 0: base_offset = 0 (swizzle anchored at 1024 B); 1: base_offset = (start >> 7) & 7
   // EPI_POST
   const float* base;
   float* x_out;
@@ -72,8 +78,6 @@ struct ConvParams {
   float* mean2;
   float gain, w_old, w_new;
 };
-
-enum { EPI_HIDDEN = 0, EPI_POST = 2 };
 
 struct ItemCoord {
   int b, y0, rcur, x0, ylo, yhi;
@@ -92,10 +96,20 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int item) 
   return c;
 }
 
+// relu(a), relu(b) (or a, b) rounded to nearest-even bf16 and packed {lo = a, hi = b}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, bool relu) {
+  uint32_t d;
+  if (relu)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 template <int CIN, int NOUT, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
-  using Cfg = ConvCfg<CIN, NOUT>;
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  using Cfg = ConvCfg<CIN, NOUT, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
@@ -111,6 +125,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: let the next layer's CTAs start their prologue as ours retire; everything below that
+  // touches memory written by an earlier kernel sits behind griddep_wait().
+  griddep_launch_dependents();
+
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&full[i], 1);
@@ -118,7 +136,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     }
     for (int i = 0; i < NACC; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one elected arrive per epilogue warp
+      mbar_init(&tempty[i], 4);  // one elected arrive per warp of the group that drains this stage
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -138,7 +156,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       // ---------------------------------------------------------------- TMA producer
       tma_prefetch_desc(&tmap);
       mbar_expect_tx(wbar, Cfg::W_BYTES);
-      bulk_load(smem_w, p.weights, Cfg::W_BYTES, wbar);
+      bulk_load(smem_w, p.weights, Cfg::W_BYTES, wbar);  // weights are constant across launches: no dependency wait
+      griddep_wait();
       uint32_t L = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
@@ -151,45 +170,50 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, NOUT);
-      const uint32_t ring_addr = smem_u32(ring), w_addr = smem_u32(smem_w);
-      mbar_wait(wbar, 0);
-      tc_fence_after();
-      uint32_t L0 = 0, T = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
-        int waited = 0;
-        const int ylast = c.y0 + c.rcur - 1;
-        for (int y = c.y0; y <= ylast; ++y, ++T) {
-          const int need = min(y + 1, c.yhi) - c.ylo + 1;
-          while (waited < need) {
-            const uint32_t q = L0 + waited;
-            mbar_wait(&full[q % NSTAGE], (q / NSTAGE) & 1);
-            ++waited;
-          }
-          const uint32_t acc = T % NACC;
-          mbar_wait(&tempty[acc], ((T / NACC) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * NOUT;
+    // ---------------------------------------------------------------- MMA issuer
+    // The whole warp walks the (warp-uniform) control flow so that barrier addresses and descriptors live in uniform
+    // registers; one elected lane issues the tcgen05 instructions.  Descriptors differ only in their 14-bit start
+    // address field, so each MMA costs two integer adds.
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, NOUT);
+    constexpr uint32_t DESC_HI = (Cfg::SBO >> 4) | (1u << 14) | (Cfg::LAYOUT << 29);  // SBO | version 1 | swizzle mode
+    const uint32_t ring_lo = (smem_u32(ring) >> 4) | 0x10000u;                         // start address >> 4 | LBO = 1
+    const uint32_t w_lo = (smem_u32(smem_w) >> 4) | 0x10000u;
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    uint32_t L0 = 0, T = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      int waited = 0;
+      const int ylast = c.y0 + c.rcur - 1;
+      for (int y = c.y0; y <= ylast; ++y, ++T) {
+        const int need = min(y + 1, c.yhi) - c.ylo + 1;
+        while (waited < need) {
+          const uint32_t q = L0 + waited;
+          mbar_wait(&full[q % NSTAGE], (q / NSTAGE) & 1);
+          ++waited;
+        }
+        const uint32_t acc = T % NACC;
+        mbar_wait(&tempty[acc], ((T / NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NOUT;
+        if (elect_one()) {
           uint32_t accumulate = 0;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const int yy = y + dy - 1;
             if (yy < 0 || yy >= p.H) continue;
             const uint32_t q = L0 + (uint32_t)(yy - c.ylo);
-            const uint32_t a_row = ring_addr + (q % NSTAGE) * Cfg::SLOT_BYTES;
+            const uint32_t a_lo = ring_lo + (q % NSTAGE) * (uint32_t)(Cfg::SLOT_BYTES >> 4);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t a0 = a_row + dx * Cfg::ROW_BYTES;
-              const uint32_t b0 = w_addr + (dy * 3 + dx) * Cfg::TAP_BYTES;
-              const uint32_t boff = p.desc_mode == 1 ? ((a0 >> 7) & 7) : 0;
+              // tap (dy, dx): the A operand is the input row shifted by dx pixels.  The swizzle pattern is anchored at
+              // absolute 1024-byte boundaries, so shifting the start address by whole 128-byte rows needs no
+              // base-offset correction (verified by psgla_selftest_umma).
 #pragma unroll
               for (int k = 0; k < Cfg::KSTEPS; ++k) {
-                const uint64_t adesc = make_smem_desc(a0 + k * 32, Cfg::SBO, Cfg::LAYOUT, boff);
-                const uint64_t bdesc = make_smem_desc(b0 + k * 32, Cfg::SBO, Cfg::LAYOUT, 0);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                const uint32_t al = a_lo + (uint32_t)((dx * Cfg::ROW_BYTES + k * 32) >> 4);
+                const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
+                umma_bf16(d_tmem, ((uint64_t)DESC_HI << 32) | al, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -199,54 +223,87 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
           if (y == ylast)
             for (int yy = y; yy <= c.yhi; ++yy) umma_commit(&empty[(L0 + (uint32_t)(yy - c.ylo)) % NSTAGE]);
         }
-        L0 += (uint32_t)(c.yhi - c.ylo + 1);
+        __syncwarp();
       }
+      L0 += (uint32_t)(c.yhi - c.ylo + 1);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
-    const int q4 = warp & 3;
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int q4 = warp & 3;  // the TMEM lane quarter this warp may read
     uint32_t T = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const ItemCoord c = decode_item(p, item);
-      const int x = c.x0 + q4 * 32 + lane;
-      const bool valid = x < p.W;
-      for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
-        const uint32_t acc = T % NACC;
-        mbar_wait(&tfull[acc], (T / NACC) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
-        if (EPI == EPI_HIDDEN) {
-          __nv_bfloat16* outp = p.out + (((size_t)c.b * p.H + y) * p.W + x) * NOUT;
+    if (EPI == EPI_POST) griddep_wait();
+    if (EPI == EPI_HIDDEN) {
+      uint8_t* stage = smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES;
+      const uint32_t stage_row = smem_u32(stage) + lane * (NOUT * 2);
+      const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+      const bool relu = p.relu != 0;
+      if (lane == 0) tma_prefetch_desc(&tmap_out);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int xw = c.x0 + q4 * 32;  // first pixel of this warp's 32-pixel box
+        for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
+          if ((int)(T & 1) != grp) continue;
+          const uint32_t acc = T % NACC;
+          mbar_wait(&tfull[acc], (T / NACC) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+          uint32_t v[NOUT];
 #pragma unroll
-          for (int half = 0; half < NOUT / 32; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr + half * 32, v);
-            tmem_ld_wait();
-            if (half == NOUT / 32 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
-            }
-            uint32_t packed[16];
+          for (int h = 0; h < NOUT / 32; ++h) tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+          tmem_ld_wait();
+          tc_fence_before();
+          // the staging box of the previous row must have been read by its TMA store before it is overwritten
+          if (lane == 0) {
+            bulk_wait_group_read0();
+            mbar_arrive(&tempty[acc]);
+          }
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float f0 = __uint_as_float(v[2 * j]) + bias_s[half * 32 + 2 * j];
-              float f1 = __uint_as_float(v[2 * j + 1]) + bias_s[half * 32 + 2 * j + 1];
-              if (p.relu) {
-                f0 = fmaxf(f0, 0.f);
-                f1 = fmaxf(f1, 0.f);
+          for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
+            const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y, relu);
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w, relu);
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y, relu);
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w, relu);
+            st_shared_v4(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4), o);  // 128B swizzle: chunk ^= row & 7
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && xw < p.W) {
+            tma_store_4d(&tmap_out, stage, 0, xw, y, c.b);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_group0();
+    } else {
+      const size_t plane = (size_t)p.H * p.W;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int x = c.x0 + q4 * 32 + lane;
+        const bool valid = x < p.W;
+        for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
+          if ((int)(T & 1) != grp) continue;
+          // fetch this pixel's base / running moments while the MMAs of the row are still in flight
+          const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
+          float bse[3] = {0.f, 0.f, 0.f}, m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              if (p.base) bse[ch] = __ldg(p.base + idx0 + ch * plane);
+              if (p.mean) {
+                m1[ch] = p.mean[idx0 + ch * plane];
+                m2[ch] = p.mean2[idx0 + ch * plane];
               }
-              __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-              packed[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(outp + half * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
             }
           }
-        } else {
+          const uint32_t acc = T % NACC;
+          mbar_wait(&tfull[acc], (T / NACC) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr, v);
           tmem_ld_wait();
@@ -254,19 +311,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
           if (valid) {
-            const size_t plane = (size_t)p.H * p.W;
-            const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
               const size_t idx = idx0 + ch * plane;
               const float r = __uint_as_float(v[ch]) + bias_s[ch];
-              const float xn = p.base ? fmaf(p.gain, r, p.base[idx]) : r;
+              const float xn = p.base ? fmaf(p.gain, r, bse[ch]) : r;
               p.x_out[idx] = xn;
               if (p.sample) p.sample[idx] = xn;
               if (p.mean) {
                 // three rounded fp32 operations each, as the reference's eager ops (restoration_algorithms.py:257-258)
-                p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, p.mean[idx]), __fmul_rn(p.w_new, xn));
-                p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, p.mean2[idx]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
+                p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, m1[ch]), __fmul_rn(p.w_new, xn));
+                p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
               }
             }
           }
@@ -296,40 +351,56 @@ PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
   return fn;
 }
 
-static int make_act_tensor_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C) {
+// Activation tensor maps (bf16 NHWC, dims {C, W, H, B}).  box_w = BOX_W: input rows with halo (OOB zero fill = the
+// convolution's zero padding); box_w = 32: one epilogue warp's output box.  Encoding costs microseconds on the host,
+// so the few (pointer, shape) combinations of a run are cached per thread.
+struct MapKey {
+  const void* ptr;
+  int B, H, W, C, box_w;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && B == o.B && H == o.H && W == o.W && C == o.C && box_w == o.box_w;
+  }
+};
+static int get_act_tensor_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int box_w) {
+  static thread_local std::vector<std::pair<MapKey, CUtensorMap>> cache;
+  const MapKey key{ptr, B, H, W, C, box_w};
+  for (const auto& e : cache)
+    if (e.first == key) {
+      *map = e.second;
+      return PSGLA_OK;
+    }
   PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
   if (!enc) return set_error(PSGLA_E_NODEVICE, "cuTensorMapEncodeTiled driver entry point not available");
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)BOX_W, 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)box_w, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapSwizzle sw = (C == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(PSGLA_E_BADARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (cache.size() >= 64) cache.erase(cache.begin());
+  cache.emplace_back(key, *map);
   return PSGLA_OK;
 }
 
-static int desc_mode_from_env() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("PSGLA_DESC_MODE");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode;
-}
-
+// Work items = (chain, 128-pixel strip, block of R output rows), dealt round-robin to one persistent CTA per SM.
+// R trades the 2 halo rows an item re-reads against the tail when items do not divide by the CTA count:
+// pick the R that minimises (items per CTA) * (R + 1).
 static void plan_items(ConvParams* p) {
   p->strips = (p->W + TILE_M - 1) / TILE_M;
   const int sms = num_sms();
   int best = 1;
+  long long best_cost = -1;
   const int cands[] = {32, 16, 8, 4, 2, 1};
   for (int R : cands) {
-    if (R > p->H && R != 1) continue;
     const long long items = (long long)p->B * p->strips * ((p->H + R - 1) / R);
-    best = R;
-    if (items >= 2LL * sms) break;
+    const long long cost = ((items + sms - 1) / sms) * (std::min(R, p->H) + 1);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = R;
+    }
   }
   const char* e = getenv("PSGLA_CONV_ROWS");
   if (e && atoi(e) > 0) best = atoi(e);
@@ -339,11 +410,17 @@ static void plan_items(ConvParams* p) {
 }
 
 template <int CIN, int NOUT, int EPI>
-static int launch_conv(const void* in, ConvParams p, cudaStream_t st) {
-  using Cfg = ConvCfg<CIN, NOUT>;
-  CUtensorMap map;
-  int rc = make_act_tensor_map(&map, in, p.B, p.H, p.W, CIN);
+static int launch_conv(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
+  using Cfg = ConvCfg<CIN, NOUT, EPI>;
+  CUtensorMap map, map_out;
+  int rc = get_act_tensor_map(&map, in, p.B, p.H, p.W, CIN, BOX_W);
   if (rc) return rc;
+  if (EPI == EPI_HIDDEN) {
+    rc = get_act_tensor_map(&map_out, out_bf16, p.B, p.H, p.W, NOUT, 32);
+    if (rc) return rc;
+  } else {
+    map_out = map;  // unused by the fused-post epilogue
+  }
   static bool attr_set = false;
   if (!attr_set) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_kernel<CIN, NOUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -351,10 +428,18 @@ static int launch_conv(const void* in, ConvParams p, cudaStream_t st) {
     attr_set = true;
   }
   plan_items(&p);
-  p.desc_mode = desc_mode_from_env();
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-  conv3x3_kernel<CIN, NOUT, EPI><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(map, p);
-  PSGLA_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_kernel<CIN, NOUT, EPI>, map, map_out, p));
   return PSGLA_OK;
 }
 
@@ -459,10 +544,10 @@ extern "C" int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer,
   cudaStream_t st = (cudaStream_t)stream;
   if (layer == depth - 1) {  // raw conv + bias -> fp32 NCHW
     p.x_out = (float*)out_dev;
-    return launch_conv<64, 16, EPI_POST>(in_dev, p, st);
+    return launch_conv<64, 16, EPI_POST>(in_dev, nullptr, p, st);
   }
-  p.out = (__nv_bfloat16*)out_dev;
-  return layer == 0 ? launch_conv<16, 64, EPI_HIDDEN>(in_dev, p, st) : launch_conv<64, 64, EPI_HIDDEN>(in_dev, p, st);
+  return layer == 0 ? launch_conv<16, 64, EPI_HIDDEN>(in_dev, out_dev, p, st)
+                    : launch_conv<64, 64, EPI_HIDDEN>(in_dev, out_dev, p, st);
 }
 
 extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgla_img_shape shape,
@@ -486,8 +571,7 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
     const LayerInfo li = layer_info(depth, l);
     ConvParams p = base_params(shape, packed, li);
     p.relu = 1;
-    p.out = (__nv_bfloat16*)ws[l & 1];
-    rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, p, st) : launch_conv<64, 64, EPI_HIDDEN>(cur, p, st);
+    rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[l & 1], p, st) : launch_conv<64, 64, EPI_HIDDEN>(cur, ws[l & 1], p, st);
     if (rc) return rc;
     cur = ws[l & 1];
   }
@@ -501,7 +585,7 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
   p.gain = post->gain;
   p.w_old = post->w_old;
   p.w_new = post->w_new;
-  return launch_conv<64, 16, EPI_POST>(cur, p, st);
+  return launch_conv<64, 16, EPI_POST>(cur, nullptr, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------ descriptor self-test
