@@ -350,6 +350,7 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": pre_gbs / peaks["hbm_gbs"], "launch_ms": pre_launch_ms},
         "state_finite": finite, "state_absmax": x_absmax,
+        "per_step_ms": [round(v, 3) for v in per_step],
     }
 
 

@@ -176,9 +176,15 @@ int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer, psgla_img_
 int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, void* out_dev, void* stream);
 
 /* tcgen05 descriptor self-test (development aid): runs a 128 x 64 x 64 GEMM tile whose A operand starts `row_shift`
- * rows into a 128B-swizzled shared-memory buffer; mode selects how the shared-memory descriptor encodes that shift.
+ * rows into a 128B-swizzled shared-memory buffer.  mode 0: A from shared memory, shift = descriptor start address;
+ * mode 1: same with a base-offset field (kept for reference, wrong on sm_100a); mode 2: A copied to tensor memory.
  * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
 int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
+
+/* tcgen05 issue-rate probe (development aid): every one of `grid` CTAs issues iters x 4 MMAs of shape M128 x n x K16
+ * (bf16, zeroed operands) back to back and writes the elapsed SM cycles to cycles_dev[block].
+ * mode 0: A and B from shared memory; 1: same with the A start address shifted by one 128-byte row; 2: A from TMEM. */
+int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -106,6 +106,118 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, bool relu) {
   return d;
 }
 
+// ------------------------------------------------------------------------------------------------ epilogues
+// Eight epilogue warps form two groups of four (one warp per TMEM lane quarter q4); group g drains the output rows
+// with T % 2 == g, where T counts the CTA's output rows in issue order and accumulator stage = T % NACC_.
+
+// Hidden layers: TMEM -> +bias -> ReLU -> bf16 -> 128B-swizzled staging box in shared memory -> one TMA store of
+// 32 pixels x NOUT channels per warp and row (clipped at the image edge by the tensor map).
+template <int NOUT, int NACC_>
+__device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUtensorMap* tmap_out, uint8_t* stage,
+                                                const float* bias_s, uint64_t* tfull, uint64_t* tempty,
+                                                uint32_t tmem_base, int grp, int q4, int lane) {
+  const uint32_t stage_row = smem_u32(stage) + lane * (NOUT * 2);
+  const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+  const bool relu = p.relu != 0;
+  if (lane == 0) tma_prefetch_desc(tmap_out);
+  uint32_t T = 0;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const ItemCoord c = decode_item(p, item);
+    const int xw = c.x0 + q4 * 32;  // first pixel of this warp's 32-pixel box
+    for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
+      if ((int)(T & 1) != grp) continue;
+      const uint32_t acc = T % NACC_;
+      mbar_wait(&tfull[acc], (T / NACC_) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+      uint32_t v[NOUT];
+#pragma unroll
+      for (int h = 0; h < NOUT / 32; ++h) tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      // the staging box of the previous row must have been read by its TMA store before it is overwritten
+      if (lane == 0) {
+        bulk_wait_group_read0();
+        mbar_arrive(&tempty[acc]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
+        const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y, relu);
+        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w, relu);
+        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y, relu);
+        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w, relu);
+        st_shared_v4(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4), o);  // 128B swizzle: chunk ^= row & 7
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && xw < p.W) {
+        tma_store_4d(tmap_out, stage, 0, xw, y, c.b);
+        bulk_commit_group();
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_group0();
+}
+
+// Last layer: the fused Langevin "post" step, fp32 NCHW (restoration_algorithms.py:238-262 / :115-135).
+template <int NOUT, int NACC_>
+__device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* bias_s, uint64_t* tfull, uint64_t* tempty,
+                                              uint32_t tmem_base, int grp, int q4, int lane) {
+  griddep_wait();  // base / running moments were written by earlier kernels
+  const size_t plane = (size_t)p.H * p.W;
+  uint32_t T = 0;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const ItemCoord c = decode_item(p, item);
+    const int x = c.x0 + q4 * 32 + lane;
+    const bool valid = x < p.W;
+    for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
+      if ((int)(T & 1) != grp) continue;
+      // fetch this pixel's base / running moments while the MMAs of the row are still in flight
+      const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
+      float bse[3] = {0.f, 0.f, 0.f}, m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          if (p.base) bse[ch] = p.base[idx0 + ch * plane];
+          if (p.mean) {
+            m1[ch] = p.mean[idx0 + ch * plane];
+            m2[ch] = p.mean2[idx0 + ch * plane];
+          }
+        }
+      }
+      const uint32_t acc = T % NACC_;
+      mbar_wait(&tfull[acc], (T / NACC_) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(taddr, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (valid) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const size_t idx = idx0 + ch * plane;
+          const float r = __uint_as_float(v[ch]) + bias_s[ch];
+          const float xn = p.base ? fmaf(p.gain, r, bse[ch]) : r;
+          p.x_out[idx] = xn;
+          if (p.sample) p.sample[idx] = xn;
+          if (p.mean) {
+            // three rounded fp32 operations each, as the reference's eager ops (restoration_algorithms.py:257-258)
+            p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, m1[ch]), __fmul_rn(p.w_new, xn));
+            p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SS kernel (A from smem)
 template <int CIN, int NOUT, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
@@ -230,110 +342,211 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
     const int ew = warp - 2;
-    const int grp = ew >> 2;
-    const int q4 = warp & 3;  // the TMEM lane quarter this warp may read
-    uint32_t T = 0;
-    if (EPI == EPI_POST) griddep_wait();
-    if (EPI == EPI_HIDDEN) {
-      uint8_t* stage = smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES;
-      const uint32_t stage_row = smem_u32(stage) + lane * (NOUT * 2);
-      const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
-      const bool relu = p.relu != 0;
-      if (lane == 0) tma_prefetch_desc(&tmap_out);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
-        const int xw = c.x0 + q4 * 32;  // first pixel of this warp's 32-pixel box
-        for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
-          if ((int)(T & 1) != grp) continue;
-          const uint32_t acc = T % NACC;
-          mbar_wait(&tfull[acc], (T / NACC) & 1);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
-          uint32_t v[NOUT];
-#pragma unroll
-          for (int h = 0; h < NOUT / 32; ++h) tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
-          tmem_ld_wait();
-          tc_fence_before();
-          // the staging box of the previous row must have been read by its TMA store before it is overwritten
-          if (lane == 0) {
-            bulk_wait_group_read0();
-            mbar_arrive(&tempty[acc]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
-            const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y, relu);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w, relu);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y, relu);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w, relu);
-            st_shared_v4(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4), o);  // 128B swizzle: chunk ^= row & 7
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && xw < p.W) {
-            tma_store_4d(&tmap_out, stage, 0, xw, y, c.b);
-            bulk_commit_group();
-          }
-        }
-      }
-      if (lane == 0) bulk_wait_group0();
-    } else {
-      const size_t plane = (size_t)p.H * p.W;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
-        const int x = c.x0 + q4 * 32 + lane;
-        const bool valid = x < p.W;
-        for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
-          if ((int)(T & 1) != grp) continue;
-          // fetch this pixel's base / running moments while the MMAs of the row are still in flight
-          const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
-          float bse[3] = {0.f, 0.f, 0.f}, m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
-          if (valid) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              if (p.base) bse[ch] = __ldg(p.base + idx0 + ch * plane);
-              if (p.mean) {
-                m1[ch] = p.mean[idx0 + ch * plane];
-                m2[ch] = p.mean2[idx0 + ch * plane];
-              }
-            }
-          }
-          const uint32_t acc = T % NACC;
-          mbar_wait(&tfull[acc], (T / NACC) & 1);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-          if (valid) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              const size_t idx = idx0 + ch * plane;
-              const float r = __uint_as_float(v[ch]) + bias_s[ch];
-              const float xn = p.base ? fmaf(p.gain, r, bse[ch]) : r;
-              p.x_out[idx] = xn;
-              if (p.sample) p.sample[idx] = xn;
-              if (p.mean) {
-                // three rounded fp32 operations each, as the reference's eager ops (restoration_algorithms.py:257-258)
-                p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, m1[ch]), __fmul_rn(p.w_new, xn));
-                p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
-              }
-            }
-          }
-        }
-      }
-    }
+    if (EPI == EPI_HIDDEN)
+      epilogue_hidden<NOUT, NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
+                                  tmem_base, ew >> 2, warp & 3, lane);
+    else
+      epilogue_post<NOUT, NACC>(p, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TS kernel (A from TMEM)
+// Measured on B200 (psgla_selftest_mma_rate): an M128 x N64 x K16 bf16 MMA takes 72 cycles with both operands in shared
+// memory (the 4 KB A fetch is exposed) but 41 cycles with A in tensor memory (floor 32).  For the 64-input-channel layers
+// four "loader" warps therefore copy every input row from the TMA ring into TMEM three times, shifted by dx = 0, 1, 2
+// pixels (TMEM lanes are pixels and cannot be shifted by the MMA), and the MMAs read A from there:
+//   TMEM columns [0, NACC_TS * NOUT)            accumulators (one stage per epilogue group)
+//                [128 + s*96 + dx*32 + k*8 ...)  A ring: slot s = input row mod 4, shift dx, K-step k (8 columns = 16 bf16)
+// Warps: 0 TMA producer, 1 MMA issuer, 2-5 loaders (TMEM lane quarter = warp & 3), 6-13 epilogue (two groups).
+constexpr int TS_NSTAGE = 4;   // shared-memory staging slots of the TMA ring
+constexpr int TS_NA = 4;       // input rows resident in TMEM
+constexpr int TS_NACC = 2;
+constexpr int TS_A_COL0 = 128;
+constexpr int TS_THREADS = 64 + 128 + 32 * EPI_WARPS;
+
+template <int NOUT, int EPI>
+struct ConvTsCfg {
+  static constexpr int ROW_BYTES = 128;
+  static constexpr int BOX_BYTES = BOX_W * ROW_BYTES;
+  static constexpr int SLOT_BYTES = round_up_c(BOX_BYTES, 1024);
+  static constexpr int TAP_BYTES = NOUT * ROW_BYTES;
+  static constexpr int W_BYTES = 9 * TAP_BYTES;
+  static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
+  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? 32 * NOUT * 2 : 0;
+  static constexpr int OFF_STAGE = OFF_RING + TS_NSTAGE * SLOT_BYTES;
+  static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + 256;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(TS_NACC * NOUT <= TS_A_COL0 && TS_A_COL0 + TS_NA * 96 <= 512, "TMEM plan does not fit 512 columns");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
+};
+
+template <int NOUT, int EPI>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  using Cfg = ConvTsCfg<NOUT, EPI>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* ring = smem + Cfg::OFF_RING;
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // TMA landed a row in the staging ring
+  uint64_t* empty = full + TS_NSTAGE;                                 // loaders have copied it out
+  uint64_t* afull = empty + TS_NSTAGE;                                // the row's three shifted copies are in TMEM
+  uint64_t* aempty = afull + TS_NA;                                   // every MMA reading them has completed
+  uint64_t* tfull = aempty + TS_NA;
+  uint64_t* tempty = tfull + TS_NACC;
+  uint64_t* wbar = tempty + TS_NACC;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TS_NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 4);
+    }
+    for (int i = 0; i < TS_NA; ++i) {
+      mbar_init(&afull[i], 4);
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < TS_NACC; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NOUT) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      tma_prefetch_desc(&tmap);
+      mbar_expect_tx(wbar, Cfg::W_BYTES);
+      bulk_load(smem_w, p.weights, Cfg::W_BYTES, wbar);
+      griddep_wait();
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
+          const uint32_t slot = L % TS_NSTAGE;
+          mbar_wait(&empty[slot], ((L / TS_NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
+          tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, y, c.b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform, one elected lane)
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, NOUT);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+    const uint32_t w_lo = (smem_u32(smem_w) >> 4) | 0x10000u;
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    uint32_t L0 = 0, T = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      int waited = 0;
+      const int ylast = c.y0 + c.rcur - 1;
+      for (int y = c.y0; y <= ylast; ++y, ++T) {
+        const int need = min(y + 1, c.yhi) - c.ylo + 1;
+        while (waited < need) {
+          const uint32_t q = L0 + waited;
+          mbar_wait(&afull[q % TS_NA], (q / TS_NA) & 1);
+          ++waited;
+        }
+        const uint32_t acc = T % TS_NACC;
+        mbar_wait(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NOUT;
+        if (elect_one()) {
+          uint32_t accumulate = 0;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int yy = y + dy - 1;
+            if (yy < 0 || yy >= p.H) continue;
+            const uint32_t q = L0 + (uint32_t)(yy - c.ylo);
+            const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
+                umma_bf16_ts(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          umma_commit(&tfull[acc]);
+          if (y - 1 >= c.ylo) umma_commit(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA]);
+          if (y == ylast)
+            for (int yy = y; yy <= c.yhi; ++yy) umma_commit(&aempty[(L0 + (uint32_t)(yy - c.ylo)) % TS_NA]);
+        }
+        __syncwarp();
+      }
+      L0 += (uint32_t)(c.yhi - c.ylo + 1);
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- loaders: staging ring -> registers -> TMEM
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;  // TMEM lane = pixel of the 128-pixel strip; box row m + dx is pixel x0 - 1 + m + dx
+    const uint32_t ring_addr = smem_u32(ring);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TS_A_COL0;
+    uint32_t L = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
+        const uint32_t slot = L % TS_NSTAGE, as = L % TS_NA;
+        mbar_wait(&full[slot], (L / TS_NSTAGE) & 1);
+        mbar_wait(&aempty[as], ((L / TS_NA) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tile = ring_addr + slot * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          uint32_t v[32];
+          ld_swizzled_row128(tile, m + dx, v);
+          tmem_st_32x32b_x32(lane_taddr + as * 96u + dx * 32u, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&empty[slot]);
+          mbar_arrive(&afull[as]);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
+    const int ew = warp - 6;
+    if (EPI == EPI_HIDDEN)
+      epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
+                                     tmem_base, ew >> 2, warp & 3, lane);
+    else
+      epilogue_post<NOUT, TS_NACC>(p, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -443,6 +656,57 @@ static int launch_conv(const void* in, void* out_bf16, ConvParams p, cudaStream_
   return PSGLA_OK;
 }
 
+template <int NOUT, int EPI>
+static int launch_conv_ts(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
+  using Cfg = ConvTsCfg<NOUT, EPI>;
+  CUtensorMap map, map_out;
+  int rc = get_act_tensor_map(&map, in, p.B, p.H, p.W, 64, BOX_W);
+  if (rc) return rc;
+  if (EPI == EPI_HIDDEN) {
+    rc = get_act_tensor_map(&map_out, out_bf16, p.B, p.H, p.W, NOUT, 32);
+    if (rc) return rc;
+  } else {
+    map_out = map;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts_kernel<NOUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  plan_items(&p);
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts_kernel<NOUT, EPI>, map, map_out, p));
+  return PSGLA_OK;
+}
+
+// A-operand source of the 64-input-channel layers: tensor memory (default) or shared memory (PSGLA_CONV_SS=1, kept for
+// A/B measurements and as the path of the 3-channel first layer).
+static bool conv_use_ts() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSGLA_CONV_SS");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+static int launch_hidden64(const void* in, void* out, const ConvParams& p, cudaStream_t st) {
+  return conv_use_ts() ? launch_conv_ts<64, EPI_HIDDEN>(in, out, p, st) : launch_conv<64, 64, EPI_HIDDEN>(in, out, p, st);
+}
+static int launch_last(const void* in, const ConvParams& p, cudaStream_t st) {
+  return conv_use_ts() ? launch_conv_ts<16, EPI_POST>(in, nullptr, p, st) : launch_conv<64, 16, EPI_POST>(in, nullptr, p, st);
+}
+
 // ---- packed weight layout: per layer [weights (9 taps, swizzled) | bias fp32], each layer 1024 B aligned
 struct LayerInfo {
   int cin, nout;  // padded
@@ -544,10 +808,9 @@ extern "C" int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer,
   cudaStream_t st = (cudaStream_t)stream;
   if (layer == depth - 1) {  // raw conv + bias -> fp32 NCHW
     p.x_out = (float*)out_dev;
-    return launch_conv<64, 16, EPI_POST>(in_dev, nullptr, p, st);
+    return launch_last(in_dev, p, st);
   }
-  return layer == 0 ? launch_conv<16, 64, EPI_HIDDEN>(in_dev, out_dev, p, st)
-                    : launch_conv<64, 64, EPI_HIDDEN>(in_dev, out_dev, p, st);
+  return layer == 0 ? launch_conv<16, 64, EPI_HIDDEN>(in_dev, out_dev, p, st) : launch_hidden64(in_dev, out_dev, p, st);
 }
 
 extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgla_img_shape shape,
@@ -571,7 +834,7 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
     const LayerInfo li = layer_info(depth, l);
     ConvParams p = base_params(shape, packed, li);
     p.relu = 1;
-    rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[l & 1], p, st) : launch_conv<64, 64, EPI_HIDDEN>(cur, ws[l & 1], p, st);
+    rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[l & 1], p, st) : launch_hidden64(cur, ws[l & 1], p, st);
     if (rc) return rc;
     cur = ws[l & 1];
   }
@@ -585,7 +848,7 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
   p.gain = post->gain;
   p.w_old = post->w_old;
   p.w_new = post->w_new;
-  return launch_conv<64, 16, EPI_POST>(cur, nullptr, p, st);
+  return launch_last(cur, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------ descriptor self-test
@@ -606,7 +869,7 @@ selftest_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tptr, 64);
+    tmem_alloc(tptr, 128);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -617,6 +880,24 @@ selftest_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     mbar_expect_tx(&bar[0], 136 * 128 + 64 * 128);
     tma_load_2d(sa, &map_a, &bar[0], 0, 0);
     tma_load_2d(sb, &map_b, &bar[0], 0, 0);
+  }
+  if (mode == 2) {
+    // A through tensor memory: every thread copies its (shifted) row into TMEM columns [64, 96), then TS MMAs
+    mbar_wait(&bar[0], 0);
+    uint32_t v[32];
+    ld_swizzled_row128(smem_u32(sa), (int)threadIdx.x + row_shift, v);
+    tmem_st_32x32b_x32(tbase + ((uint32_t)(warp * 32) << 16) + 64, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ts(tbase, tbase + 64 + k * 8, make_smem_desc(smem_u32(sb) + k * 32, 1024, LAYOUT_SW128, 0), idesc, k > 0);
+      umma_commit(&bar[1]);
+    }
+  } else if (threadIdx.x == 0) {
     mbar_wait(&bar[0], 0);
     tc_fence_after();
     const uint32_t a0 = smem_u32(sa) + row_shift * 128, b0 = smem_u32(sb);
@@ -639,7 +920,7 @@ selftest_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tbase, 64);
+    tmem_dealloc(tbase, 128);
   }
 }
 }  // namespace psgla
@@ -676,6 +957,81 @@ extern "C" int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* 
     attr_set = true;
   }
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, d_dev, row_shift, mode);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA rate probe
+namespace psgla {
+// One CTA per block issues `iters` x 4 K-steps of M128 x N x K16 bf16 MMAs back to back on zeroed operands and reports
+// the cycles one MMA took.  mode 0: A and B from shared memory (SS); 1: SS with the A start address shifted by one
+// 128-byte row (the conv kernel's dx tap shift); 2: A from tensor memory (TS).
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n, int iters, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;                 // 136 rows x 128 B
+  uint8_t* sb = smem + 18 * 1024;     // 256 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 52 * 1024);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 52 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, n);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+    const uint32_t a_lo = ((smem_u32(sa) + (mode == 1 ? 128u : 0u)) >> 4) | 0x10000u;
+    const uint32_t b_lo = (smem_u32(sb) >> 4) | 0x10000u;
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (mode == 2)
+            umma_bf16_ts(tbase, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+          else
+            umma_bf16(tbase, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    if (elect_one()) cycles[blockIdx.x] = t0 ? (t1 - t0) : 0;
+    // only the elected lane took t0
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tbase, 512);
+  }
+}
+}  // namespace psgla
+
+extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream) {
+  PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,
+                "psgla_selftest_mma_rate: bad argument");
+  const int smem = 54 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  mma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(mode, n, iters, cycles_dev);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
 }

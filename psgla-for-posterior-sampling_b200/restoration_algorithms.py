@@ -68,6 +68,10 @@ class _Run:
         self.samples = torch.empty((max(n_samples, 1),) + tuple(self.X.shape), dtype=torch.float32, device=self.device)
         self.mean = torch.zeros_like(self.X)
         self.mean2 = torch.zeros_like(self.X)
+        # closed windows are copied into storage reserved in chunks, so that no allocator call (a device-wide
+        # synchronisation when it reaches cudaMalloc) lands inside the iteration loop
+        self._win_left = self.n_iter // (self.n_inter_mmse + 1)
+        self._win_chunk, self._win_used = None, 0
         self.Xlist, self.Xlist_mmse, self.Xlist_mmse2 = [], [], []
         self.iter_mmse = 0
         self.seed = 0 if seed is None else int(seed)
@@ -135,8 +139,18 @@ class _Run:
         if self.iter_mmse <= self.n_inter_mmse - 1:
             self.iter_mmse += 1
         else:
-            self.Xlist_mmse.append(self._out(self.mean.clone()))
-            self.Xlist_mmse2.append(self._out(self.mean2.clone()))
+            if self._win_chunk is None or self._win_used == self._win_chunk.shape[0]:
+                per_window = 2 * self.mean.numel() * 4
+                n = max(1, min(max(self._win_left, 1), (1 << 31) // per_window))
+                self._win_chunk = torch.empty((n, 2) + tuple(self.mean.shape), dtype=torch.float32, device=self.device)
+                self._win_used = 0
+            slot = self._win_chunk[self._win_used]
+            self._win_used += 1
+            self._win_left -= 1
+            slot[0].copy_(self.mean)
+            slot[1].copy_(self.mean2)
+            self.Xlist_mmse.append(self._out(slot[0]))
+            self.Xlist_mmse2.append(self._out(slot[1]))
             self.iter_mmse = 0  # the next update has w_old = 0, which restarts the window without a memset
 
 

@@ -141,6 +141,110 @@ def check_gmm_speed():
             print("gmm speed %s chains=%d: %.3f ms for 2000 steps -> %.3e chain-steps/s" % (alg, nc, ms, nc * 2000 / ms * 1e3), flush=True)
 
 
+def check_iter_breakdown():
+    """Where one PSGLA image iteration spends its time: per-kernel CUDA-event timings, with and without an L2 flush."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    B, H, W = int(os.environ.get("DIAG_B", "32")), 256, 256
+    dev = torch.device("cuda")
+    den = P.DnCNN(pretrained=P.random_dncnn_state_dict(0, scale=0.5), device=dev)
+    im = torch.rand(1, 3, H, W, device=dev)
+    dg, init, y, mask = P.make_inpainting(im, 0.5, 1.0, 0)
+    s = 2 / 255
+    run = P.psgla_run(init, dg, den, 1.0, 5.0, s, s * s, n_iter=1000, n_inter=10, n_inter_mmse=10, seed=0, n_chains=B)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    shape = P._lib.ImgShape(B, 3, H, W)
+    ws, den_in = den.buffers(shape)
+    half = (B * H * W * 64 * 2 + 1023) // 1024 * 1024
+    bufs = [ws.data_ptr(), ws.data_ptr() + half]
+    out = torch.empty(B, 3, H, W, device=dev)
+
+    def timed(fn, reps=10, do_flush=False):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            if do_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps * 1e3
+
+    it = [0]
+
+    def step():
+        run.step(it[0])
+        it[0] += 1
+
+    print("B=%d step            : %8.1f us   (with L2 flush %8.1f us)" % (B, timed(step), timed(step, do_flush=True)), flush=True)
+    print("pre                  : %8.1f us" % timed(lambda: run.pre(0, run.pre_params)), flush=True)
+    conv = lambda l, i, o: P._lib.check(lib.psgla_conv3x3_layer(den.packed.data_ptr(), 20, l, shape, i, o, 1, None), "conv")
+    print("layer 0 (3->64, SS)  : %8.1f us" % timed(lambda: conv(0, den_in.data_ptr(), bufs[0])), flush=True)
+    print("layer 5 (64->64)     : %8.1f us   (flush %8.1f us)" % (timed(lambda: conv(5, bufs[0], bufs[1])),
+                                                                   timed(lambda: conv(5, bufs[0], bufs[1]), do_flush=True)), flush=True)
+    print("layer 19 (64->3 raw) : %8.1f us" % timed(lambda: conv(19, bufs[1], out.data_ptr())), flush=True)
+    post = P._lib.PostParams(1.0, 0.5, 0.5)
+    print("dncnn+post (20 conv) : %8.1f us" % timed(lambda: den.residual_post(shape, den_in, run.base, post, run.X, None, run.mean, run.mean2)), flush=True)
+
+    def hidden18():
+        for l in range(1, 19):
+            conv(l, bufs[l & 1], bufs[(l + 1) & 1])
+    print("18 hidden layers     : %8.1f us" % timed(hidden18), flush=True)
+
+
+def check_step_series():
+    """Per-iteration device time of the first 80 PSGLA iterations after start-up (clock / power ramp effects)."""
+    import subprocess as sp
+    import torch
+    import psgla_b200 as P
+    B, H, W = int(os.environ.get("DIAG_B", "32")), 256, 256
+    dev = torch.device("cuda")
+    den = P.DnCNN(pretrained=P.random_dncnn_state_dict(0, scale=0.5), device=dev)
+    im = torch.rand(1, 3, H, W, device=dev)
+    dg, init, y, mask = P.make_inpainting(im, 0.5, 1.0, 0)
+    s = 2 / 255
+    run = P.psgla_run(init, dg, den, 1.0, 5.0, s, s * s, n_iter=1000, n_inter=10, n_inter_mmse=10, seed=0, n_chains=B)
+    torch.cuda.synchronize()
+    smi = sp.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader",
+                    "-lms", "20"], stdout=sp.PIPE, text=True)
+    ev = []
+    for i in range(80):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run.step(i)
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    import time
+    time.sleep(0.1)
+    smi.terminate()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    print("step ms:", " ".join("%.2f" % m for m in ms), flush=True)
+    print("clocks:", " | ".join(l.strip() for l in smi.stdout.read().splitlines()[:40]), flush=True)
+
+
+def check_mma_rate():
+    """Cycles per tcgen05.mma (M128 x N x K16 bf16) for SS / shifted-SS / TS operand sources, one CTA and all SMs."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    iters = 2000
+    for grid in (1, 148):
+        out = torch.zeros(grid, dtype=torch.int64, device="cuda")
+        for mode, name in ((0, "SS"), (1, "SS+128B"), (2, "TS")):
+            row = []
+            for n in (16, 32, 64, 96, 128, 192, 256):
+                P._lib.check(lib.psgla_selftest_mma_rate(mode, n, iters, grid, out.data_ptr(), None), "mma_rate")
+                torch.cuda.synchronize()
+                row.append("N=%d: %.1f" % (n, out.double().mean().item() / (iters * 4)))
+            print("mma_rate grid=%d %-8s cycles/MMA  %s" % (grid, name, "  ".join(row)), flush=True)
+
+
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
 
 if __name__ == "__main__":

@@ -39,12 +39,13 @@ def test_umma_descriptor_selftest():
     torch.manual_seed(0)
     a = torch.randn(136, 64, device="cuda").to(torch.bfloat16).contiguous()
     b = torch.randn(64, 64, device="cuda").to(torch.bfloat16).contiguous()
-    for shift in (0, 1, 2, 5, 8):
-        d = torch.zeros(128, 64, device="cuda")
-        P._lib.check(lib.psgla_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), shift, 0, None), "selftest")
-        torch.cuda.synchronize()
-        ref = a[shift:shift + 128].float() @ b.float().t()
-        assert (d - ref).abs().max().item() < 1e-4
+    for mode in (0, 2):  # A operand from shared memory (descriptor shift) / from tensor memory (copied by tcgen05.st)
+        for shift in (0, 1, 2, 5, 8):
+            d = torch.zeros(128, 64, device="cuda")
+            P._lib.check(lib.psgla_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), shift, mode, None), "selftest")
+            torch.cuda.synchronize()
+            ref = a[shift:shift + 128].float() @ b.float().t()
+            assert (d - ref).abs().max().item() < 1e-4, (mode, shift)
 
 
 @pytest.mark.parametrize("B,H,W,layer", [(1, 8, 128, 1), (2, 40, 256, 5), (1, 33, 200, 3), (3, 5, 17, 2), (1, 1, 1, 4),
