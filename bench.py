@@ -59,6 +59,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, the samplers' reference-style prints)
+# write to file descriptor 1 too, so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -468,7 +488,7 @@ def run_reference(args):
                              **cpu_baseline_image(args, n_iter=12)}
         except Exception as exc:  # noqa: BLE001
             line["image"] = {"impl": "reference", "error": repr(exc)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_block(args):
@@ -501,6 +521,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    capture_stdout()
     if args.only_image:
         args.chains, args.chain_steps, args.steps, args.skip_cpu = 4096, 16, 1, True
 
@@ -568,7 +589,7 @@ def main():
                 img["cpu_baseline"] = cpu_baseline_image(args)
             except Exception as exc:  # noqa: BLE001
                 img["cpu_baseline"] = {"error": repr(exc)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if ws > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
