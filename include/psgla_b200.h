@@ -181,6 +181,14 @@ int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, void* out_dev
  * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
 int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
 
+/* One general convolution layer of the DRUNet denoiser (deepinv.models.DRUNet, sampling_images.py:136) as implicit GEMM:
+ *   mode 0: 3x3 stride 1 zero-pad 1 (Cin -> Cout); 1: 2x2 stride 2 (downsampling); 2: 2x2 stride 2 transposed (upsampling).
+ * in_dev bf16 NHWC [B][Hin][Win][Cin]; w_dev bf16 [taps][Cout][Cin] (taps = 9 / 4 / 4, tap = ky * kw + kx);
+ * out_dev bf16 NHWC of extent Hin x Win / Hin/2 x Win/2 / 2Hin x 2Win; res1_dev / res2_dev: optional tensors of the
+ * output's shape that are added before the optional ReLU.  Channels are multiples of 64; no bias (DRUNet has none). */
+int psgla_convg_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const void* w_dev, const void* in_dev,
+                      const void* res1_dev, const void* res2_dev, void* out_dev, int relu, void* stream);
+
 /* tcgen05 issue-rate probe (development aid): every one of `grid` CTAs issues iters x 4 MMAs of shape M128 x n x K16
  * (bf16, zeroed operands) back to back and writes the elapsed SM cycles to cycles_dev[block].
  * mode 0: A and B from shared memory; 1: same with the A start address shifted by one 128-byte row; 2: A from TMEM. */

@@ -86,6 +86,73 @@ def make_dncnn_weights(seed=0, lipschitz=0.9, n_power_iter=30, spatial=32):
     return {k: v.detach().clone().float() for k, v in net.state_dict().items()}
 
 
+class _ResBlock(nn.Module):
+    """KAIR ``ResBlock(mode='CRC', bias=False)``: x + conv(relu(conv(x))); parameters live under ``res.0`` / ``res.2``."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.res = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.ReLU(inplace=False), nn.Conv2d(c, c, 3, 1, 1, bias=False))
+
+    def forward(self, x):
+        return x + self.res(x)
+
+
+class DRUNet(nn.Module):
+    """``deepinv.models.DRUNet(in_channels=3, out_channels=3)`` as constructed at sampling_images.py:136 -- the DPIR
+    network of Zhang et al. (KAIR ``UNetRes``: nc=[64,128,256,512], nb=4, act 'R', strideconv down, convtranspose up,
+    no biases), restated from its published definition because deepinv 0.2.1 is absent (PARITY UNPINNED against
+    deepinv).  ``forward(x, sigma)`` concatenates a constant noise-level channel and returns the *denoised image*
+    (no global residual).  State-dict keys follow the ``drunet_color.pth`` checkpoint: ``m_head``, ``m_down{1,2,3}.{0..3}
+    .res.{0,2}``, ``m_down{k}.4`` (2x2 stride-2 conv), ``m_body.{0..3}``, ``m_up{k}.0`` (2x2 stride-2 transposed conv),
+    ``m_up{k}.{1..4}``, ``m_tail``.  H and W must be multiples of 8 (deepinv pads internally; the rule is unverifiable
+    here, so callers crop)."""
+
+    def __init__(self, in_channels=3, out_channels=3, nc=(64, 128, 256, 512), nb=4):
+        super().__init__()
+        self.m_head = nn.Conv2d(in_channels + 1, nc[0], 3, 1, 1, bias=False)
+        self.m_down1 = nn.Sequential(*[_ResBlock(nc[0]) for _ in range(nb)], nn.Conv2d(nc[0], nc[1], 2, 2, 0, bias=False))
+        self.m_down2 = nn.Sequential(*[_ResBlock(nc[1]) for _ in range(nb)], nn.Conv2d(nc[1], nc[2], 2, 2, 0, bias=False))
+        self.m_down3 = nn.Sequential(*[_ResBlock(nc[2]) for _ in range(nb)], nn.Conv2d(nc[2], nc[3], 2, 2, 0, bias=False))
+        self.m_body = nn.Sequential(*[_ResBlock(nc[3]) for _ in range(nb)])
+        self.m_up3 = nn.Sequential(nn.ConvTranspose2d(nc[3], nc[2], 2, 2, 0, bias=False), *[_ResBlock(nc[2]) for _ in range(nb)])
+        self.m_up2 = nn.Sequential(nn.ConvTranspose2d(nc[2], nc[1], 2, 2, 0, bias=False), *[_ResBlock(nc[1]) for _ in range(nb)])
+        self.m_up1 = nn.Sequential(nn.ConvTranspose2d(nc[1], nc[0], 2, 2, 0, bias=False), *[_ResBlock(nc[0]) for _ in range(nb)])
+        self.m_tail = nn.Conv2d(nc[0], out_channels, 3, 1, 1, bias=False)
+
+    def forward(self, x, sigma):
+        if isinstance(sigma, torch.Tensor):
+            sigma = float(sigma.reshape(-1)[0])
+        noise_map = torch.full((x.shape[0], 1, x.shape[2], x.shape[3]), float(sigma), dtype=x.dtype, device=x.device)
+        x0 = torch.cat((x, noise_map), 1)
+        x1 = self.m_head(x0)
+        x2 = self.m_down1(x1)
+        x3 = self.m_down2(x2)
+        x4 = self.m_down3(x3)
+        h = self.m_body(x4)
+        h = self.m_up3(h + x4)
+        h = self.m_up2(h + x3)
+        h = self.m_up1(h + x2)
+        return self.m_tail(h + x1)
+
+
+def make_drunet_weights(seed=0, gain=0.5):
+    """Seeded random-init DRUNet state dict (checkpoints are unreachable offline).  Uniform +-gain*sqrt(3/fan_in) keeps
+    activations O(1) through the 4 x 4 residual blocks per scale; the tail is scaled down so that D(x) stays near the
+    input range.  Deterministic; the oracle and the CUDA path consume the same fp32 tensors."""
+    g = torch.Generator().manual_seed(seed)
+    net = DRUNet()
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            fan_in = p.shape[1] * p.shape[2] * p.shape[3] if not name.startswith("m_up") or ".res." in name else p.shape[0] * 4
+            bound = gain * math.sqrt(3.0 / fan_in)
+            if ".res.2." in name:
+                bound *= 0.5  # second conv of a residual block: keep the branch a perturbation of the identity
+            if name.startswith("m_tail"):
+                bound *= 0.25
+            p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+    return {k: v.detach().clone().float() for k, v in net.state_dict().items()}
+
+
 # ----------------------------------------------------------------------------- operators
 
 

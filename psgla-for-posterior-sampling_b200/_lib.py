@@ -68,6 +68,7 @@ SIGNATURES = {
     "psgla_conv3x3_layer": (_int, [_vp, _int, _int, ImgShape, _vp, _vp, _int, _vp]),
     "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, _vp, _vp]),
     "psgla_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
+    "psgla_convg_layer": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "psgla_selftest_mma_rate": (_int, [_int, _int, _int, _int, _vp, _vp]),
 }
 

@@ -1,0 +1,378 @@
+// General convolution layers of the DRUNet denoiser as implicit GEMM on tcgen05 tensor cores (sm_100a):
+//   CG_CONV3  3x3, stride 1, zero padding 1, C -> C      (the residual blocks at 128 / 256 / 512 channels)
+//   CG_DOWN2  2x2, stride 2, no padding,     C -> 2C     (KAIR "strideconv" downsampling)
+//   CG_UP2    2x2, stride 2 transposed,      C -> C/2    (KAIR "convtranspose" upsampling; four 1x1 GEMMs, one per
+//                                                          output quadrant (dy, dx))
+// Replaces the cuDNN fp32 convolutions behind deepinv.models.DRUNet.forward (constructed at sampling_images.py:136,
+// called at restoration_algorithms.py:238); architecture restated in oracle/image_oracle.py (KAIR UNetRes).
+//
+// Unlike the 64-channel layers (conv_tc.cu), the weights of these layers (up to 9 x 512 x 512 bf16 = 4.7 MB) do not fit
+// in shared memory, so both operands stream: for every (tap, 64-channel block) the TMA producer loads an A box
+// (128 "tile pixels" x 64 channels; PX pixels x ROWS image rows, shifted by the tap, OOB zero fill = conv padding) and
+// a B box (N_TILE output channels x 64) into a ring; one elected thread issues 4 K16 MMAs per box into a TMEM
+// accumulator; 8 epilogue warps add the residual inputs, apply ReLU, convert to bf16 and store NHWC.
+// Activations bf16 NHWC [B][H][W][C]; weights bf16 [tap][Cout][Cin].
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace psgla {
+using namespace sm100;
+
+enum { CG_CONV3 = 0, CG_DOWN2 = 1, CG_UP2 = 2 };
+
+constexpr int CG_EPI_WARPS = 8;
+constexpr int CG_THREADS = 64 + 32 * CG_EPI_WARPS;
+constexpr int CG_NACC = 2;
+
+template <int N_TILE>
+struct CgCfg {
+  static constexpr int A_BYTES = 128 * 128;     // 128 tile pixels x 64 channels bf16
+  static constexpr int B_BYTES = N_TILE * 128;  // N_TILE output channels x 64 input channels bf16
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = (CG_NACC * N_TILE) < 32 ? 32 : CG_NACC * N_TILE;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+};
+
+struct CgParams {
+  int mode, taps, kblocks;
+  int B, Hin, Win, Cin, Cout;
+  int Hg, Wg;      // pixel grid the M tiles cover: the output grid (CONV3, DOWN2) or the input grid (UP2)
+  int Hout, Wout;  // output tensor extent
+  int PX, ROWS;    // tile = PX pixels x ROWS rows (PX * ROWS <= 128)
+  int tiles_x, tiles_y, n_tiles_n, quads, n_items;
+  int relu;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  __nv_bfloat16* out;
+};
+
+struct CgItem {
+  int b, y0, x0, n0, q;
+};
+__device__ __forceinline__ CgItem cg_decode(const CgParams& p, int item) {
+  CgItem c;
+  const int inner = p.quads * p.n_tiles_n;
+  const int sub = item % inner;
+  int t = item / inner;
+  c.q = sub / p.n_tiles_n;
+  c.n0 = (sub % p.n_tiles_n);
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  c.b = t / p.tiles_y;
+  c.x0 = tx * p.PX;
+  c.y0 = ty * p.ROWS;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t cg_pack(float a, float b, bool relu) {
+  uint32_t d;
+  if (relu)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void cg_add_bf16x8(float (&f)[8], const uint4 r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] += __uint_as_float(w[i] << 16);
+    f[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(CG_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const CgParams p) {
+  using Cfg = CgCfg<N_TILE>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tfull = empty + NSTAGE;
+  uint64_t* tempty = tfull + CG_NACC;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty + CG_NACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < CG_NACC; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int kiters = p.taps * p.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_w);
+      griddep_wait();
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const CgItem c = cg_decode(p, item);
+        for (int t = 0; t < p.taps; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++L) {
+            const uint32_t slot = L % NSTAGE;
+            mbar_wait(&empty[slot], ((L / NSTAGE) & 1) ^ 1);
+            uint8_t* sa = smem + slot * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full[slot], (uint32_t)(p.PX * p.ROWS * 128 + Cfg::B_BYTES));
+            if (p.mode == CG_CONV3) {
+              tma_load_4d(sa, &map_a, &full[slot], kb * 64, c.x0 + (t % 3) - 1, c.y0 + (t / 3) - 1, c.b);
+              tma_load_3d(sb, &map_w, &full[slot], kb * 64, c.n0 * N_TILE, t);
+            } else if (p.mode == CG_DOWN2) {
+              // input viewed as {C, 2 (dx), Win/2, 2 (dy), B * Hin/2}
+              tma_load_5d(sa, &map_a, &full[slot], kb * 64, t & 1, c.x0, t >> 1, c.b * (p.Hin / 2) + c.y0);
+              tma_load_3d(sb, &map_w, &full[slot], kb * 64, c.n0 * N_TILE, t);
+            } else {
+              tma_load_4d(sa, &map_a, &full[slot], kb * 64, c.x0, c.y0, c.b);
+              tma_load_3d(sb, &map_w, &full[slot], kb * 64, c.n0 * N_TILE, c.q);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform, one elected lane)
+    constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+    const uint32_t smem_lo = (smem_u32(smem) >> 4) | 0x10000u;
+    uint32_t L = 0, T = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++T) {
+      const uint32_t acc = T % CG_NACC;
+      mbar_wait(&tempty[acc], ((T / CG_NACC) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      for (int it = 0; it < kiters; ++it, ++L) {
+        const uint32_t slot = L % NSTAGE;
+        mbar_wait(&full[slot], (L / NSTAGE) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = smem_lo + slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc,
+                      (it | k) != 0);
+          umma_commit(&empty[slot]);
+          if (it == kiters - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;  // tile pixel
+    const int r = m / p.PX, px = m % p.PX;
+    const bool relu = p.relu != 0;
+    griddep_wait();
+    uint32_t T = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++T) {
+      if ((int)(T & 1) != grp) continue;
+      const CgItem c = cg_decode(p, item);
+      const uint32_t acc = T % CG_NACC;
+      const int yg = c.y0 + r, xg = c.x0 + px;
+      const bool valid = (m < p.PX * p.ROWS) && yg < p.Hg && xg < p.Wg;
+      int yo = yg, xo = xg;
+      if (p.mode == CG_UP2) {
+        yo = 2 * yg + (c.q >> 1);
+        xo = 2 * xg + (c.q & 1);
+      }
+      const size_t off = (((size_t)c.b * p.Hout + yo) * p.Wout + xo) * p.Cout + (size_t)c.n0 * N_TILE;
+      mbar_wait(&tfull[acc], (T / CG_NACC) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * N_TILE;
+#pragma unroll 1
+      for (int ch = 0; ch < N_TILE / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == N_TILE / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // 16-byte chunk = 8 channels
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
+            const size_t o = off + ch * 32 + j * 8;
+            if (p.res1) cg_add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res1 + o));
+            if (p.res2) cg_add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + o));
+            uint4 w;
+            w.x = cg_pack(f[0], f[1], relu);
+            w.y = cg_pack(f[2], f[3], relu);
+            w.z = cg_pack(f[4], f[5], relu);
+            w.w = cg_pack(f[6], f[7], relu);
+            *reinterpret_cast<uint4*>(p.out + o) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int cg_encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box) {
+  PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return set_error(PSGLA_E_NODEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PSGLA_E_BADARG, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+  return PSGLA_OK;
+}
+
+struct CgMapKey {
+  const void* ptr;
+  int a, b, c, d, e, f;
+  bool operator==(const CgMapKey& o) const {
+    return ptr == o.ptr && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e && f == o.f;
+  }
+};
+static int cg_cached_map(CUtensorMap* map, const CgMapKey& key, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                         const cuuint32_t* box) {
+  static thread_local std::vector<std::pair<CgMapKey, CUtensorMap>> cache;
+  for (const auto& e : cache)
+    if (e.first == key) {
+      *map = e.second;
+      return PSGLA_OK;
+    }
+  int rc = cg_encode(map, key.ptr, rank, dims, strides, box);
+  if (rc) return rc;
+  if (cache.size() >= 256) cache.erase(cache.begin());
+  cache.emplace_back(key, *map);
+  return PSGLA_OK;
+}
+
+template <int N_TILE>
+static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParams& p, cudaStream_t st) {
+  using Cfg = CgCfg<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CG_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE>, ma, mw, p));
+  return PSGLA_OK;
+}
+
+// One layer.  in: bf16 NHWC [B][Hin][Win][Cin]; w: bf16 [taps][Cout][Cin]; out: bf16 NHWC (CONV3: same extent, DOWN2:
+// half, UP2: double); res1 / res2: optional tensors of the output's shape added before the optional ReLU.
+int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const void* w, const void* in, const void* res1,
+                    const void* res2, void* out, int relu, cudaStream_t st) {
+  PSGLA_REQUIRE(mode >= CG_CONV3 && mode <= CG_UP2, "conv_gemm_layer: unknown mode %d", mode);
+  PSGLA_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0,
+                "conv_gemm_layer: channels must be multiples of 64 (got %d -> %d), extents positive", Cin, Cout);
+  PSGLA_REQUIRE(w && in && out, "conv_gemm_layer: null pointer");
+  PSGLA_REQUIRE(mode != CG_DOWN2 || (Hin % 2 == 0 && Win % 2 == 0), "stride-2 conv needs even extents (got %d x %d)", Hin, Win);
+  CgParams p{};
+  p.mode = mode;
+  p.taps = mode == CG_CONV3 ? 9 : (mode == CG_DOWN2 ? 4 : 1);
+  p.quads = mode == CG_UP2 ? 4 : 1;
+  p.kblocks = Cin / 64;
+  p.B = B, p.Hin = Hin, p.Win = Win, p.Cin = Cin, p.Cout = Cout;
+  p.Hg = mode == CG_DOWN2 ? Hin / 2 : Hin;
+  p.Wg = mode == CG_DOWN2 ? Win / 2 : Win;
+  p.Hout = mode == CG_UP2 ? 2 * Hin : p.Hg;
+  p.Wout = mode == CG_UP2 ? 2 * Win : p.Wg;
+  p.PX = std::min(p.Wg, 128);
+  p.ROWS = std::max(1, std::min(128 / p.PX, p.Hg));
+  p.tiles_x = (p.Wg + p.PX - 1) / p.PX;
+  p.tiles_y = (p.Hg + p.ROWS - 1) / p.ROWS;
+  const int n_tile = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  p.n_tiles_n = Cout / n_tile;
+  p.n_items = B * p.tiles_y * p.tiles_x * p.quads * p.n_tiles_n;
+  p.relu = relu;
+  p.res1 = (const __nv_bfloat16*)res1;
+  p.res2 = (const __nv_bfloat16*)res2;
+  p.out = (__nv_bfloat16*)out;
+
+  CUtensorMap ma, mw;
+  int rc;
+  if (mode == CG_DOWN2) {
+    const cuuint64_t dims[5] = {(cuuint64_t)Cin, 2, (cuuint64_t)(Win / 2), 2, (cuuint64_t)B * (Hin / 2)};
+    const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 4, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Win * Cin * 4};
+    const cuuint32_t box[5] = {64, 1, (cuuint32_t)p.PX, 1, (cuuint32_t)p.ROWS};
+    rc = cg_cached_map(&ma, CgMapKey{in, 5, B, Hin, Win, Cin, p.PX * 1000 + p.ROWS}, 5, dims, strides, box);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p.PX, (cuuint32_t)p.ROWS, 1};
+    rc = cg_cached_map(&ma, CgMapKey{in, 4, B, Hin, Win, Cin, p.PX * 1000 + p.ROWS}, 4, dims, strides, box);
+  }
+  if (rc) return rc;
+  {
+    const int taps_total = mode == CG_UP2 ? 4 : p.taps;
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps_total};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+    rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, Cout, taps_total, n_tile, 0}, 3, dims, strides, box);
+  }
+  if (rc) return rc;
+  if (n_tile == 256) return cg_launch<256>(ma, mw, p, st);
+  if (n_tile == 128) return cg_launch<128>(ma, mw, p, st);
+  return cg_launch<64>(ma, mw, p, st);
+}
+
+}  // namespace psgla
+
+using namespace psgla;
+
+extern "C" int psgla_convg_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const void* w_dev, const void* in_dev,
+                                 const void* res1_dev, const void* res2_dev, void* out_dev, int relu, void* stream) {
+  return conv_gemm_layer(mode, B, Hin, Win, Cin, Cout, w_dev, in_dev, res1_dev, res2_dev, out_dev, relu, (cudaStream_t)stream);
+}
