@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PSGLA_ABI_VERSION 1
+#define PSGLA_ABI_VERSION 2
 
 enum {
   PSGLA_OK = 0,
@@ -40,6 +40,9 @@ enum {
 
 const char* psgla_last_error(void);
 int psgla_abi_version(void);
+/* sizeof() of the structs below as the library was compiled (0: psgla_gmm2d_problem, 1: psgla_img_shape, 2: psgla_pre_params,
+ * 3: psgla_post_params; -1 otherwise) -- lets a binding verify its struct layout. */
+int psgla_struct_size(int which);
 /* compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
 int psgla_device_arch(void);
 
@@ -114,6 +117,9 @@ typedef struct psgla_pre_params {
   float noise_scale;  /* sqrt(2) s  resp.  sqrt(2 delta) */
   float proj_gain;    /* PnP-ULA: delta / lambd; PSGLA: 0 */
   float c_min, c_max; /* PnP-ULA projection box, restoration_algorithms.py:38 defaults -1, 2 */
+  float x_gain;       /* base += x_gain * X: PnP-ULA with a non-residual denoiser (DRUNet) needs -delta*alpha/s2 here
+                         because alpha (D(X) - X)/s2 is no longer a pure function of the network output; else 0 */
+  float den_in_c3;    /* value written to channel 3 of den_in: the DRUNet noise-level map (sigma); 0 for DnCNN */
   uint64_t seed;
   int64_t chain_id0;
   int64_t iteration;
@@ -156,6 +162,8 @@ size_t psgla_dncnn_workspace_bytes(psgla_img_shape shape);
  *                  three rounded fp32 operations each, like the reference's eager ops) */
 typedef struct psgla_post_params {
   float gain;
+  float base_scale;   /* DRUNet path only: X+ = base_scale * base + gain * D(den_in)  (PSGLA: 1 - alpha, alpha);
+                         the DnCNN path is residual (X+ = base + gain * R) and ignores it */
   float w_old, w_new; /* iter_mmse/(iter_mmse+1), 1/(iter_mmse+1) as float */
 } psgla_post_params;
 
@@ -172,14 +180,28 @@ int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgla_img_shape
 int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer, psgla_img_shape shape, const void* in_dev,
                         void* out_dev, int relu, void* stream);
 
-/* Layout helper: fp32 NCHW [B][3][H][W] -> bf16 NHWC [B][H][W][16]. */
-int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, void* out_dev, void* stream);
+/* Layout helper: fp32 NCHW [B][3][H][W] -> bf16 NHWC [B][H][W][16]; channel 3 = c3 (the DRUNet noise-level map, 0 for
+ * DnCNN), channels 4..15 zero. */
+int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, float c3, void* out_dev, void* stream);
 
 /* tcgen05 descriptor self-test (development aid): runs a 128 x 64 x 64 GEMM tile whose A operand starts `row_shift`
  * rows into a 128B-swizzled shared-memory buffer.  mode 0: A from shared memory, shift = descriptor start address;
  * mode 1: same with a base-offset field (kept for reference, wrong on sm_100a); mode 2: A copied to tensor memory.
  * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
 int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
+
+/* DRUNet (deepinv.models.DRUNet(in_channels=3, out_channels=3), sampling_images.py:136; KAIR UNetRes nc = 64/128/256/512,
+ * nb = 4, no biases).  weights_host: psgla_drunet_num_weights() = 64 fp32 tensors in state-dict order (m_head, m_down1.*,
+ * m_down2.*, m_down3.*, m_body.*, m_up3.*, m_up2.*, m_up1.*, m_tail; torch layouts).  den_in_dev: bf16 NHWC16 as written by a
+ * "pre" call with den_in_c3 = sigma.  H and W must be multiples of 8.
+ * psgla_drunet_denoise_post: X+ = post->base_scale * base + post->gain * DRUNet(den_in), thinning and moments as above. */
+int psgla_drunet_num_weights(void);
+size_t psgla_drunet_packed_bytes(void);
+int psgla_drunet_pack_weights(const float* const* weights_host, void* packed_dev, void* stream);
+size_t psgla_drunet_workspace_bytes(psgla_img_shape shape);
+int psgla_drunet_denoise_post(const void* packed_dev, psgla_img_shape shape, const void* den_in_dev, void* workspace_dev,
+                              size_t workspace_bytes, const float* base_dev, const psgla_post_params* post,
+                              float* x_out_dev, float* sample_dev, float* mean_dev, float* mean2_dev, void* stream);
 
 /* One general convolution layer of the DRUNet denoiser (deepinv.models.DRUNet, sampling_images.py:136) as implicit GEMM:
  *   mode 0: 3x3 stride 1 zero-pad 1 (Cin -> Cout); 1: 2x2 stride 2 (downsampling); 2: 2x2 stride 2 transposed (upsampling).

@@ -7,7 +7,8 @@ directory name carries the reference's name and is not a Python identifier).
 """
 from . import _lib  # noqa: F401
 from . import dist  # noqa: F401
-from .denoisers import DnCNN, lipschitz_dncnn_state_dict, random_dncnn_state_dict  # noqa: F401
+from .denoisers import (DRUNET_KEYS, DRUNet, DnCNN, lipschitz_dncnn_state_dict, random_dncnn_state_dict,  # noqa: F401
+                        random_drunet_state_dict)  # noqa: F401
 from .operators import (DeblurDataGrad, InpaintingDataGrad, PriorGrad, blur_taps, make_deblurring,  # noqa: F401
                         make_inpainting)
 from .restoration_algorithms import pnp_ula, pnpula, pnpula_run, psgla, psgla_run  # noqa: F401

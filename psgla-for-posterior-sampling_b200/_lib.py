@@ -36,13 +36,14 @@ class ImgShape(C.Structure):
 class PreParams(C.Structure):
     """psgla_pre_params"""
     _fields_ = [("alg", C.c_int32), ("gain_data", C.c_float), ("noise_scale", C.c_float), ("proj_gain", C.c_float),
-                ("c_min", C.c_float), ("c_max", C.c_float), ("seed", C.c_uint64), ("chain_id0", C.c_int64),
+                ("c_min", C.c_float), ("c_max", C.c_float), ("x_gain", C.c_float), ("den_in_c3", C.c_float),
+                ("seed", C.c_uint64), ("chain_id0", C.c_int64),
                 ("iteration", C.c_int64)]
 
 
 class PostParams(C.Structure):
     """psgla_post_params"""
-    _fields_ = [("gain", C.c_float), ("w_old", C.c_float), ("w_new", C.c_float)]
+    _fields_ = [("gain", C.c_float), ("base_scale", C.c_float), ("w_old", C.c_float), ("w_new", C.c_float)]
 
 
 _vp, _i64, _u64, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_size_t
@@ -52,6 +53,7 @@ SIGNATURES = {
     "psgla_last_error": (C.c_char_p, []),
     "psgla_abi_version": (_int, []),
     "psgla_device_arch": (_int, []),
+    "psgla_struct_size": (_int, [_int]),
     "psgla_gmm2d_run": (_int, [C.POINTER(GmmProblem), _int, _vp, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _i64, _vp]),
     "psgla_gmm2d_denoise": (_int, [C.POINTER(GmmProblem), C.c_double, _int, _vp, _vp, _i64, _vp]),
     "psgla_gmm2d_noise": (_int, [_vp, _i64, _i64, _i64, _i64, _u64, _vp]),
@@ -66,7 +68,12 @@ SIGNATURES = {
     "psgla_dncnn_residual_post": (_int, [_int, _vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp,
                                          _vp, _vp]),
     "psgla_conv3x3_layer": (_int, [_vp, _int, _int, ImgShape, _vp, _vp, _int, _vp]),
-    "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, _vp, _vp]),
+    "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, C.c_float, _vp, _vp]),
+    "psgla_drunet_num_weights": (_int, []),
+    "psgla_drunet_packed_bytes": (_sz, []),
+    "psgla_drunet_pack_weights": (_int, [C.POINTER(C.POINTER(C.c_float)), _vp, _vp]),
+    "psgla_drunet_workspace_bytes": (_sz, [ImgShape]),
+    "psgla_drunet_denoise_post": (_int, [_vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp, _vp, _vp]),
     "psgla_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "psgla_convg_layer": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "psgla_selftest_mma_rate": (_int, [_int, _int, _int, _int, _vp, _vp]),
@@ -91,6 +98,10 @@ def lib() -> C.CDLL:
                     fn = getattr(handle, name)  # AttributeError if the header and the library disagree
                     fn.restype = res
                     fn.argtypes = args
+                for which, struct in enumerate((GmmProblem, ImgShape, PreParams, PostParams)):
+                    if handle.psgla_struct_size(which) != C.sizeof(struct):
+                        raise RuntimeError("ctypes layout of %s (%d bytes) disagrees with libpsgla_b200.so (%d bytes): "
+                                           "rebuild the library" % (struct.__name__, C.sizeof(struct), handle.psgla_struct_size(which)))
                 _lib = handle
     return _lib
 

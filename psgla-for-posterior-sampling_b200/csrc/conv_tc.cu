@@ -43,6 +43,16 @@ constexpr int round_up_c(int v, int a) { return (v + a - 1) / a * a; }
 
 enum { EPI_HIDDEN = 0, EPI_POST = 2 };
 
+// f[0..7] += eight bf16 values packed in a 16-byte vector
+__device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4 r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] += __uint_as_float(w[i] << 16);
+    f[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
 template <int CIN, int NOUT, int EPI>
 struct ConvCfg {
   static constexpr int ROW_BYTES = CIN * 2;
@@ -70,13 +80,16 @@ struct ConvParams {
   const uint8_t* weights;  // 9 taps, swizzled
   const float* bias;       // NOUT floats
   int relu;
+  // EPI_HIDDEN: optional bf16 NHWC tensors of the output's shape added before the ReLU (DRUNet residual / skip adds)
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
   // EPI_POST
   const float* base;
   float* x_out;
   float* sample;
   float* mean;
   float* mean2;
-  float gain, w_old, w_new;
+  float gain, base_scale, w_old, w_new;
 };
 
 struct ItemCoord {
@@ -141,14 +154,24 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
         mbar_arrive(&tempty[acc]);
       }
       __syncwarp();
+      const bool has_res = p.res1 != nullptr && xw + lane < p.W;
+      const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
 #pragma unroll
       for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
         const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+        float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                      __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                      __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                      __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+        if (has_res) {
+          add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res1 + roff + 8 * j));
+          if (p.res2) add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j));
+        }
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y, relu);
-        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w, relu);
-        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y, relu);
-        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w, relu);
+        o.x = pack_bf16x2(f[0], f[1], relu);
+        o.y = pack_bf16x2(f[2], f[3], relu);
+        o.z = pack_bf16x2(f[4], f[5], relu);
+        o.w = pack_bf16x2(f[6], f[7], relu);
         st_shared_v4(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4), o);  // 128B swizzle: chunk ^= row & 7
       }
       fence_proxy_async();
@@ -203,7 +226,7 @@ __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* 
         for (int ch = 0; ch < 3; ++ch) {
           const size_t idx = idx0 + ch * plane;
           const float r = __uint_as_float(v[ch]) + bias_s[ch];
-          const float xn = p.base ? fmaf(p.gain, r, bse[ch]) : r;
+          const float xn = p.base ? fmaf(p.gain, r, p.base_scale * bse[ch]) : r;
           p.x_out[idx] = xn;
           if (p.sample) p.sample[idx] = xn;
           if (p.mean) {
@@ -740,6 +763,8 @@ static inline uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
+void pack_conv3x3_swizzled(const float* w, int nout_real, int cin_real, int nout_pad, int cin_pad, uint8_t* dst);
+
 }  // namespace psgla
 
 using namespace psgla;
@@ -754,20 +779,9 @@ extern "C" int psgla_dncnn_pack_weights(int depth, const float* const* weights_h
     const LayerInfo li = layer_info(depth, l);
     const int cin_real = (l == 0) ? 3 : 64;
     const int nout_real = (l == depth - 1) ? 3 : 64;
-    const int row_bytes = li.cin * 2;
     const float* w = weights_host[l];  // OIHW [nout_real][cin_real][3][3]
     PSGLA_REQUIRE(w != nullptr, "layer %d: null weight pointer", l);
-    for (int tap = 0; tap < 9; ++tap)
-      for (int n = 0; n < nout_real; ++n)
-        for (int k = 0; k < cin_real; ++k) {
-          const float val = w[((size_t)n * cin_real + k) * 9 + tap];
-          const int kbyte = k * 2;
-          int chunk = kbyte >> 4;
-          chunk ^= (row_bytes == 128) ? (n & 7) : ((n >> 2) & 1);
-          const size_t phys = li.w_off + (size_t)tap * li.nout * row_bytes + (size_t)n * row_bytes + chunk * 16 + (kbyte & 15);
-          const uint16_t h = f32_to_bf16_rn(val);
-          std::memcpy(&host[phys], &h, 2);
-        }
+    pack_conv3x3_swizzled(w, nout_real, cin_real, li.nout, li.cin, host.data() + li.w_off);
     if (biases_host && biases_host[l])
       std::memcpy(&host[li.b_off], biases_host[l], (size_t)nout_real * 4);
   }
@@ -846,10 +860,75 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
   p.mean = mean_dev;
   p.mean2 = mean2_dev;
   p.gain = post->gain;
+  p.base_scale = 1.0f;  // DnCNN is a residual denoiser: X+ = base + gain * R
   p.w_old = post->w_old;
   p.w_new = post->w_new;
   return launch_last(cur, p, st);
 }
+
+
+// ------------------------------------------------------------------------------------------------ internal API (drunet.cu)
+namespace psgla {
+
+// fp32 OIHW [nout_real][cin_real][3][3] -> bf16 [tap][nout_pad][cin_pad], 128B- (cin_pad = 64) or 32B- (16) swizzled as the
+// resident-weight kernels expect; dst must be zero-initialised (padding rows / channels stay zero).
+void pack_conv3x3_swizzled(const float* w, int nout_real, int cin_real, int nout_pad, int cin_pad, uint8_t* dst) {
+  const int row_bytes = cin_pad * 2;
+  for (int tap = 0; tap < 9; ++tap)
+    for (int n = 0; n < nout_real; ++n)
+      for (int k = 0; k < cin_real; ++k) {
+        const float val = w[((size_t)n * cin_real + k) * 9 + tap];
+        const int kbyte = k * 2;
+        int chunk = kbyte >> 4;
+        chunk ^= (row_bytes == 128) ? (n & 7) : ((n >> 2) & 1);
+        const size_t phys = (size_t)tap * nout_pad * row_bytes + (size_t)n * row_bytes + chunk * 16 + (kbyte & 15);
+        const uint16_t h = f32_to_bf16_rn(val);
+        std::memcpy(dst + phys, &h, 2);
+      }
+}
+
+int conv64_hidden(const void* in, void* out, const uint8_t* w, const float* bias, int B, int H, int W, int relu,
+                  const void* res1, const void* res2, cudaStream_t st) {
+  ConvParams p{};
+  p.B = B, p.H = H, p.W = W;
+  p.weights = w;
+  p.bias = bias;
+  p.relu = relu;
+  p.res1 = (const __nv_bfloat16*)res1;
+  p.res2 = (const __nv_bfloat16*)res2;
+  return launch_hidden64(in, out, p, st);
+}
+
+int conv_first16(const void* in16, void* out, const uint8_t* w, const float* bias, int B, int H, int W, int relu,
+                 cudaStream_t st) {
+  ConvParams p{};
+  p.B = B, p.H = H, p.W = W;
+  p.weights = w;
+  p.bias = bias;
+  p.relu = relu;
+  return launch_conv<16, 64, EPI_HIDDEN>(in16, out, p, st);
+}
+
+int conv_last_post(const void* in, const uint8_t* w, const float* bias, int B, int H, int W, const float* base,
+                   float base_scale, float gain, float w_old, float w_new, float* x_out, float* sample, float* mean,
+                   float* mean2, cudaStream_t st) {
+  ConvParams p{};
+  p.B = B, p.H = H, p.W = W;
+  p.weights = w;
+  p.bias = bias;
+  p.base = base;
+  p.base_scale = base_scale;
+  p.gain = gain;
+  p.w_old = w_old;
+  p.w_new = w_new;
+  p.x_out = x_out;
+  p.sample = sample;
+  p.mean = mean;
+  p.mean2 = mean2;
+  return launch_last(in, p, st);
+}
+
+}  // namespace psgla
 
 // ------------------------------------------------------------------------------------------------ descriptor self-test
 namespace psgla {

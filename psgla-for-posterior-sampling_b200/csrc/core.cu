@@ -30,3 +30,15 @@ extern "C" int psgla_device_arch(void) {
     return psgla::set_error(PSGLA_E_NODEVICE, "cannot query compute capability");
   return major * 10 + minor;
 }
+
+// sizeof() of the ABI structs as this library was compiled, for binding self-checks (0: gmm2d_problem, 1: img_shape,
+// 2: pre_params, 3: post_params).
+extern "C" int psgla_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(psgla_gmm2d_problem);
+    case 1: return (int)sizeof(psgla_img_shape);
+    case 2: return (int)sizeof(psgla_pre_params);
+    case 3: return (int)sizeof(psgla_post_params);
+    default: return -1;
+  }
+}

@@ -27,7 +27,7 @@ __device__ __forceinline__ float normal_at(uint64_t seed, uint64_t chain, uint32
 
 struct PreArgs {
   int alg;
-  float gain_data, noise_scale, proj_gain, c_min, c_max;
+  float gain_data, noise_scale, proj_gain, c_min, c_max, x_gain, den_in_c3;
   unsigned long long seed;
   long long chain_id0;
   unsigned int iteration;
@@ -35,7 +35,7 @@ struct PreArgs {
 
 __device__ __forceinline__ float langevin_base(const PreArgs& a, float x, float neg_grad_unscaled, float z) {
   // neg_grad_unscaled = mask (x - y)  resp.  A^T(A x - y); the data term is  -gain_data * that.
-  float base = fmaf(-a.gain_data, neg_grad_unscaled, x);
+  float base = fmaf(-a.gain_data, neg_grad_unscaled, fmaf(a.x_gain, x, x));
   if (a.alg == PSGLA_ALG_PNPULA) {
     const float proj = fminf(fmaxf(x, a.c_min), a.c_max);
     base = fmaf(-a.proj_gain, x - proj, base);
@@ -43,9 +43,9 @@ __device__ __forceinline__ float langevin_base(const PreArgs& a, float x, float 
   return fmaf(a.noise_scale, z, base);
 }
 
-__device__ __forceinline__ void store_nhwc16(__nv_bfloat16* dst_pixel, float c0, float c1, float c2) {
+__device__ __forceinline__ void store_nhwc16(__nv_bfloat16* dst_pixel, float c0, float c1, float c2, float c3) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(c0, c1);
-  const __nv_bfloat162 b = __floats2bfloat162_rn(c2, 0.f);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(c2, c3);
   uint4* d = reinterpret_cast<uint4*>(dst_pixel);
   d[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b), 0u, 0u);
   d[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -107,7 +107,7 @@ pre_inpaint_kernel(PreArgs a, int B, int H, int W, const float* __restrict__ x, 
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j)
-    store_nhwc16(den_in + ((long long)b * plane + pix + j) * 16, outv[0][j], outv[1][j], outv[2][j]);
+    store_nhwc16(den_in + ((long long)b * plane + pix + j) * 16, outv[0][j], outv[1][j], outv[2][j], a.den_in_c3);
 }
 
 // ------------------------------------------------------------------------------------------------ blur / deblur pre
@@ -222,7 +222,8 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gx = x0 + pcol + j;
-    if (gx < W) store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx) * 16, xin[0][j], xin[1][j], xin[2][j]);
+    if (gx < W)
+      store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx) * 16, xin[0][j], xin[1][j], xin[2][j], a.den_in_c3);
   }
 }
 
@@ -242,13 +243,13 @@ noise_kernel(int B, long long chw, unsigned long long seed, long long chain_id0,
 }
 
 __global__ void __launch_bounds__(256)
-to_nhwc16_kernel(int B, int H, int W, const float* __restrict__ x, __nv_bfloat16* __restrict__ out) {
+to_nhwc16_kernel(int B, int H, int W, const float* __restrict__ x, float c3, __nv_bfloat16* __restrict__ out) {
   const long long plane = (long long)H * W;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= plane * B) return;
   const long long b = g / plane, pix = g % plane;
   const float* xp = x + b * 3 * plane + pix;
-  store_nhwc16(out + g * 16, xp[0], xp[plane], xp[2 * plane]);
+  store_nhwc16(out + g * 16, xp[0], xp[plane], xp[2 * plane], c3);
 }
 
 static int fill_pre(const psgla_pre_params* p, PreArgs* a) {
@@ -261,6 +262,8 @@ static int fill_pre(const psgla_pre_params* p, PreArgs* a) {
   a->proj_gain = p->proj_gain;
   a->c_min = p->c_min;
   a->c_max = p->c_max;
+  a->x_gain = p->x_gain;
+  a->den_in_c3 = p->den_in_c3;
   a->seed = p->seed;
   a->chain_id0 = p->chain_id0;
   a->iteration = (unsigned int)p->iteration;
@@ -369,12 +372,12 @@ extern "C" int psgla_img_noise(psgla_img_shape s, uint64_t seed, int64_t chain_i
   return PSGLA_OK;
 }
 
-extern "C" int psgla_img_to_nhwc16(psgla_img_shape s, const float* x_dev, void* out_dev, void* stream) {
+extern "C" int psgla_img_to_nhwc16(psgla_img_shape s, const float* x_dev, float c3, void* out_dev, void* stream) {
   int rc = check_img(s);
   if (rc) return rc;
   PSGLA_REQUIRE(x_dev && out_dev, "psgla_img_to_nhwc16: null pointer");
   const long long n = (long long)s.H * s.W * s.B;
-  to_nhwc16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s.B, s.H, s.W, x_dev,
+  to_nhwc16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s.B, s.H, s.W, x_dev, c3,
                                                                                  (__nv_bfloat16*)out_dev);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;

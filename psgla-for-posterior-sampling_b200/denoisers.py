@@ -15,7 +15,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["DnCNN", "random_dncnn_state_dict", "lipschitz_dncnn_state_dict"]
+__all__ = ["DnCNN", "DRUNet", "random_dncnn_state_dict", "lipschitz_dncnn_state_dict", "random_drunet_state_dict",
+           "DRUNET_KEYS"]
 
 
 def random_dncnn_state_dict(seed=0, depth=20, nf=64, scale=1.0):
@@ -64,6 +65,8 @@ def lipschitz_dncnn_state_dict(seed=0, depth=20, nf=64, lipschitz=0.9, spatial=1
 
 
 class DnCNN:
+    is_residual = True  # D(x) = x + R(x): the samplers add gain * R to their base
+
     def __init__(self, in_channels=3, out_channels=3, depth=20, bias=True, nf=64, pretrained=None, device=None):
         torch_ = _lib.require_cuda()
         if in_channels != 3 or out_channels != 3 or nf != 64:
@@ -128,9 +131,131 @@ class DnCNN:
         _, den_in = self.buffers(shape)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().psgla_img_to_nhwc16(shape, _lib.ptr(x), _lib.ptr(den_in), _lib.stream_ptr(self.device)),
+            _lib.check(_lib.lib().psgla_img_to_nhwc16(shape, _lib.ptr(x), 0.0, _lib.ptr(den_in), _lib.stream_ptr(self.device)),
                        "psgla_img_to_nhwc16")
-        self.residual_post(shape, den_in, x, _lib.PostParams(1.0, 0.0, 1.0), out)
+        self.residual_post(shape, den_in, x, _lib.PostParams(1.0, 1.0, 0.0, 1.0), out)
+        return out
+
+    __call__ = forward
+    apply_post = residual_post  # common name used by the samplers for both denoiser families
+
+
+# ----------------------------------------------------------------------------------------------------- DRUNet
+def _drunet_keys(nb=4):
+    keys = ["m_head.weight"]
+    for s in (1, 2, 3):
+        keys += ["m_down%d.%d.res.%d.weight" % (s, i, j) for i in range(nb) for j in (0, 2)] + ["m_down%d.%d.weight" % (s, nb)]
+    keys += ["m_body.%d.res.%d.weight" % (i, j) for i in range(nb) for j in (0, 2)]
+    for s in (3, 2, 1):
+        keys += ["m_up%d.0.weight" % s] + ["m_up%d.%d.res.%d.weight" % (s, i, j) for i in range(1, nb + 1) for j in (0, 2)]
+    return keys + ["m_tail.weight"]
+
+
+DRUNET_KEYS = _drunet_keys()  # the 64 weight tensors of drunet_color.pth in state-dict order
+
+
+def _drunet_shape(key, nc=(64, 128, 256, 512)):
+    if key == "m_head.weight":
+        return (nc[0], 4, 3, 3)
+    if key == "m_tail.weight":
+        return (3, nc[0], 3, 3)
+    if key.startswith("m_body"):
+        return (nc[3], nc[3], 3, 3)
+    s = int(key[len("m_down")]) if key.startswith("m_down") else int(key[len("m_up")])
+    if ".res." in key:
+        return (nc[s - 1], nc[s - 1], 3, 3)
+    if key.startswith("m_down"):
+        return (nc[s], nc[s - 1], 2, 2)  # strided conv, OIHW
+    return (nc[s], nc[s - 1], 2, 2)      # transposed conv: [Cin][Cout][2][2]
+
+
+def random_drunet_state_dict(seed=0, gain=0.5):
+    """Seeded random-init DRUNet state dict on the CPU (checkpoints are unreachable offline): uniform
+    +-gain*sqrt(3/fan_in), second conv of every residual block halved, tail quartered, so activations stay O(1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in DRUNET_KEYS:
+        shp = _drunet_shape(k)
+        is_up = k.startswith("m_up") and ".res." not in k
+        fan_in = shp[0] * 4 if is_up else shp[1] * shp[2] * shp[3]
+        bound = gain * math.sqrt(3.0 / fan_in)
+        if ".res.2." in k:
+            bound *= 0.5
+        if k == "m_tail.weight":
+            bound *= 0.25
+        sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
+    return sd
+
+
+class DRUNet:
+    """``deepinv.models.DRUNet(in_channels=3, out_channels=3, pretrained=..., device=...)`` (sampling_images.py:136) on
+    tcgen05 convolutions: the DPIR U-Net (KAIR UNetRes, nc = 64/128/256/512, 4 residual blocks per stage, no biases).
+    ``forward(x, sigma)`` appends the constant noise-level channel and returns the denoised image.  ``pretrained``: a
+    ``drunet_color.pth``-style state dict / path, or None for seeded random init.  H, W multiples of 8."""
+
+    is_residual = False  # the network outputs D(x) itself
+
+    def __init__(self, in_channels=3, out_channels=3, pretrained=None, device=None):
+        torch_ = _lib.require_cuda()
+        if in_channels != 3 or out_channels != 3:
+            raise ValueError("the sm_100a DRUNet path is built for colour images: in = out = 3 channels")
+        self.device = torch_.device("cuda", torch_.cuda.current_device()) if device is None else torch_.device(device)
+        if pretrained is None:
+            sd = random_drunet_state_dict(0)
+        elif isinstance(pretrained, str):
+            sd = torch_.load(pretrained, map_location="cpu")
+        else:
+            sd = pretrained
+        missing = [k for k in DRUNET_KEYS if k not in sd]
+        if missing:
+            raise KeyError("state dict lacks %s" % missing[:3])
+        ws = []
+        for k in DRUNET_KEYS:
+            w = sd[k].detach().to("cpu", torch_.float32).contiguous()
+            if tuple(w.shape) != _drunet_shape(k):
+                raise ValueError("%s has shape %s, expected %s" % (k, tuple(w.shape), _drunet_shape(k)))
+            ws.append(w)
+        self.state_dict_fp32 = dict(zip(DRUNET_KEYS, ws))
+        lib = _lib.lib()
+        assert lib.psgla_drunet_num_weights() == len(ws)
+        self.packed = torch_.empty(lib.psgla_drunet_packed_bytes(), dtype=torch_.uint8, device=self.device)
+        FP = C.POINTER(C.c_float)
+        warr = (FP * len(ws))(*[C.cast(w.data_ptr(), FP) for w in ws])
+        with torch_.cuda.device(self.device):
+            _lib.check(lib.psgla_drunet_pack_weights(warr, _lib.ptr(self.packed), _lib.stream_ptr(self.device)),
+                       "psgla_drunet_pack_weights")
+        self._ws = None
+        self._den_in = None
+
+    def buffers(self, shape: "_lib.ImgShape"):
+        need = _lib.lib().psgla_drunet_workspace_bytes(shape)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        n_in = shape.B * shape.H * shape.W * 16
+        if self._den_in is None or self._den_in.numel() < n_in:
+            self._den_in = torch.empty(n_in, dtype=torch.bfloat16, device=self.device)
+        return self._ws, self._den_in
+
+    def apply_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None):
+        ws, _ = self.buffers(shape)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().psgla_drunet_denoise_post(_lib.ptr(self.packed), shape, _lib.ptr(den_in), _lib.ptr(ws), ws.numel(),
+                                                      _lib.ptr(base), C.byref(post), _lib.ptr(x_out), _lib.ptr(sample),
+                                                      _lib.ptr(mean), _lib.ptr(mean2), _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_drunet_denoise_post")
+
+    def forward(self, x, sigma):
+        if not x.is_cuda:
+            raise RuntimeError("DRUNet.forward needs a CUDA tensor: there is no CPU path")
+        sigma = float(sigma.reshape(-1)[0]) if isinstance(sigma, torch.Tensor) else float(sigma)
+        x = x.to(torch.float32).contiguous()
+        shape = _lib.ImgShape(int(x.shape[0]), 3, int(x.shape[2]), int(x.shape[3]))
+        _, den_in = self.buffers(shape)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().psgla_img_to_nhwc16(shape, _lib.ptr(x), sigma, _lib.ptr(den_in), _lib.stream_ptr(self.device)),
+                       "psgla_img_to_nhwc16")
+        self.apply_post(shape, den_in, x, _lib.PostParams(1.0, 0.0, 0.0, 1.0), out)  # out = 0 * x + 1 * D(x)
         return out
 
     __call__ = forward

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .denoisers import DnCNN
+from .denoisers import DRUNet, DnCNN
 from .operators import DeblurDataGrad, InpaintingDataGrad, PriorGrad
 
 __all__ = ["psgla", "pnpula", "pnp_ula", "psgla_run", "pnpula_run"]
@@ -42,8 +42,8 @@ class _Run:
         if not isinstance(data_grad, (InpaintingDataGrad, DeblurDataGrad)):
             raise TypeError("data_grad must be an InpaintingDataGrad or DeblurDataGrad (structured callable); an opaque "
                             "callable cannot be fused into the CUDA kernels and there is no eager fallback")
-        if not isinstance(denoiser, DnCNN):
-            raise TypeError("denoiser must be a psgla_b200.DnCNN")
+        if not isinstance(denoiser, (DnCNN, DRUNet)):
+            raise TypeError("denoiser must be a psgla_b200.DnCNN or psgla_b200.DRUNet")
         if seed is None and noise is None:
             raise ValueError("seed=None: the reference fails with UnboundLocalError here "
                              "(restoration_algorithms.py:211-213,232); pass a seed or a noise tensor")
@@ -93,8 +93,8 @@ class _Run:
             self.y = data_grad.y.to(self.device).expand(-1, 3, -1, -1).contiguous()
             self.mask = data_grad.mask.to(self.device).expand(-1, 3, -1, -1).contiguous()
 
-    def configure(self, pre, gain):
-        self.pre_params, self.gain = pre, float(gain)
+    def configure(self, pre, gain, base_scale=1.0):
+        self.pre_params, self.gain, self.base_scale = pre, float(gain), float(base_scale)
 
     def step(self, i):
         """Iteration i of the sampler: fused Langevin "pre" kernel, then DnCNN + fused "post" epilogue."""
@@ -130,9 +130,9 @@ class _Run:
 
     def post(self, i, gain):
         k = self.iter_mmse
-        post = _lib.PostParams(float(gain), float(np.float32(k / (k + 1))), float(np.float32(1 / (k + 1))))
+        post = _lib.PostParams(float(gain), self.base_scale, float(np.float32(k / (k + 1))), float(np.float32(1 / (k + 1))))
         sample = self.samples[i // self.n_inter] if i % self.n_inter == 0 else None
-        self.den.residual_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2)
+        self.den.apply_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2)
         if sample is not None:
             self.Xlist.append(self._out(sample))
         # window bookkeeping exactly as restoration_algorithms.py:128-144 / :255-271
@@ -172,8 +172,13 @@ def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4
     pre.alg = _lib.ALG_PSGLA
     pre.gain_data = (delta32 / _f(lambd)) / run.dg.sigma2
     pre.noise_scale = float(np.float32(np.float32(np.sqrt(2)) * np.float32(sig32)))
-    pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0
-    run.configure(pre, _f(alpha))  # (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
+    pre.proj_gain, pre.c_min, pre.c_max, pre.x_gain = 0.0, 0.0, 0.0, 0.0
+    if denoiser.is_residual:  # DnCNN: (1-alpha) Y + alpha (Y + R(Y)) = Y + alpha R(Y)
+        pre.den_in_c3 = 0.0
+        run.configure(pre, _f(alpha))
+    else:  # DRUNet: (1-alpha) Y + alpha D(Y; sig) with the noise-level map sig in channel 3 (restoration_algorithms.py:238)
+        pre.den_in_c3 = sig32
+        run.configure(pre, _f(alpha), 1.0 - _f(alpha))
     return run
 
 
@@ -206,7 +211,12 @@ def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1
     pre.noise_scale = float(np.float32(math.sqrt(2 * delta_f)))
     pre.proj_gain = delta_f / lambd_f
     pre.c_min, pre.c_max = float(c_min), float(c_max)
-    run.configure(pre, delta_f * prior_grad.alpha / prior_grad.s2)
+    g = delta_f * prior_grad.alpha / prior_grad.s2  # delta * prior_grad = g (D(X; s1) - X)   (sampling_images.py:156-157)
+    if prior_grad.denoiser.is_residual:
+        pre.x_gain, pre.den_in_c3 = 0.0, 0.0  # D(X) - X is the network output itself
+    else:
+        pre.x_gain, pre.den_in_c3 = -g, prior_grad.s1
+    run.configure(pre, g)
     return run
 
 

@@ -188,7 +188,7 @@ def check_iter_breakdown():
     print("layer 5 (64->64)     : %8.1f us   (flush %8.1f us)" % (timed(lambda: conv(5, bufs[0], bufs[1])),
                                                                    timed(lambda: conv(5, bufs[0], bufs[1]), do_flush=True)), flush=True)
     print("layer 19 (64->3 raw) : %8.1f us" % timed(lambda: conv(19, bufs[1], out.data_ptr())), flush=True)
-    post = P._lib.PostParams(1.0, 0.5, 0.5)
+    post = P._lib.PostParams(1.0, 1.0, 0.5, 0.5)
     print("dncnn+post (20 conv) : %8.1f us" % timed(lambda: den.residual_post(shape, den_in, run.base, post, run.X, None, run.mean, run.mean2)), flush=True)
 
     def hidden18():

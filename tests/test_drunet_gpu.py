@@ -89,3 +89,90 @@ def test_convg_argument_errors():
     assert lib.psgla_convg_layer(0, 1, 4, 4, 48, 64, t.data_ptr(), t.data_ptr(), None, None, t.data_ptr(), 0, None) == -1
     assert lib.psgla_convg_layer(1, 1, 5, 4, 64, 128, t.data_ptr(), t.data_ptr(), None, None, t.data_ptr(), 0, None) == -1
     assert lib.psgla_convg_layer(7, 1, 4, 4, 64, 64, t.data_ptr(), t.data_ptr(), None, None, t.data_ptr(), 0, None) == -1
+
+
+# ----------------------------------------------------------------------------------------------------- whole network
+from oracle import image_oracle as io_  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def drunets():
+    sd = io_.make_drunet_weights(seed=0)
+    den = P.DRUNet(pretrained=sd)
+    net = io_.DRUNet().cuda()
+    net.load_state_dict(sd)
+    net.eval()
+    return den, net
+
+
+def test_product_and_oracle_random_init_agree():
+    """The product's own seeded random init is the oracle's (same generator stream, same scaling)."""
+    a, b = P.random_drunet_state_dict(3), io_.make_drunet_weights(seed=3)
+    assert list(a) == list(b) == P.DRUNET_KEYS
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 40, 72), (1, 256, 256)])
+def test_drunet_forward_against_fp32_oracle(drunets, B, H, W):
+    den, net = drunets
+    x = torch.rand(B, 3, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    sigma = 5.0 / 255.0
+    with torch.no_grad():
+        ref = net(x, sigma)
+    got = den.forward(x, sigma)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    # ~70 bf16 layers against fp32: relative error of the output stays at the percent level
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 3e-2, rel
+    assert (got - ref).abs().max().item() < 5e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_drunet_rejects_sizes_not_multiple_of_8(drunets):
+    den, _ = drunets
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        den.forward(torch.rand(1, 3, 36, 64, device="cuda"), 0.02)
+
+
+def test_psgla_drunet_replay_against_oracle(drunets):
+    """PSGLA with the non-residual denoiser: X+ = (1 - alpha) Y + alpha D(Y; s) (restoration_algorithms.py:238)."""
+    den, net = drunets
+    torch.manual_seed(0)
+    im = torch.rand(1, 3, 32, 48, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("psgla", den="DRUNet", lambd=25.0)
+    n_iter = 6
+    g = torch.Generator(device="cuda").manual_seed(0)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    for alpha in (1.0, 0.7):
+        kw = dict(alpha=torch.tensor(alpha, device="cuda"), lambd=torch.tensor(prm["lambd"], device="cuda"),
+                  sig_float=prm["s"], delta=prm["delta"], n_iter=n_iter, n_inter=2, n_inter_mmse=2, seed=0)
+        Xr, Mr, M2r = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw)
+        Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
+        torch.cuda.synchronize()
+        assert len(Xr) == len(Xg) and len(Mr) == len(Mg) == len(M2g)
+        for a, b in zip(Xr + Mr, Xg + Mg):
+            assert (a - b).abs().max().item() < 2e-2
+
+
+def test_pnpula_drunet_replay_against_oracle(drunets):
+    """PnP-ULA with prior_grad = alpha (D(X; s1) - X) / s2 (sampling_images.py:156-157) and a non-residual denoiser."""
+    den, net = drunets
+    torch.manual_seed(1)
+    im = torch.rand(1, 3, 32, 32, device="cuda")
+    dg, init, y = P.make_deblurring(im, l=2, blur_type="gaussian", si=1.0, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("pnp_ula", den="DRUNet", s=5.0)
+    n_iter = 5
+    g = torch.Generator(device="cuda").manual_seed(0)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    delta = torch.tensor(prm["delta"], device="cuda", dtype=torch.float32)
+    lambd = torch.tensor(prm["lambd"], device="cuda", dtype=torch.float32)
+    pg_ref = io_.make_prior_grad(net, 1.0, prm["s1"], prm["s2"], device="cuda")
+    pg = P.PriorGrad(den, 1.0, prm["s1"], prm["s2"])
+    Xr, Mr, _ = io_.pnpula(init, dg, pg_ref, delta, lambd, n_iter=n_iter, n_inter=1, n_inter_mmse=1, seed=0, device="cuda", noise=noise)
+    Xg, Mg, _ = P.pnpula(init, dg, pg, delta, lambd, n_iter=n_iter, n_inter=1, n_inter_mmse=1, seed=0, noise=noise)
+    torch.cuda.synchronize()
+    assert len(Xr) == len(Xg) and len(Mr) == len(Mg)
+    for a, b in zip(Xr + Mr, Xg + Mg):
+        assert (a - b).abs().max().item() < 2e-2
