@@ -52,6 +52,7 @@ MUFU_PER_CHAIN_STEP = 7
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.5; no measured FP32 figure in MEASURED_PEAKS.json
 DNCNN_FLOP_PER_PIXEL = 2 * 9 * (3 * 64 + 18 * 64 * 64 + 64 * 3)  # 1 334 016
 CONV64_FLOP_PER_PIXEL = 2 * 9 * 64 * 64  # 73 728, one hidden layer
+DRUNET_FLOP_PER_PIXEL = 4235136  # head 4 608 + 3 x 16 x 73 728 + 8 x 73 728 + 6 x 16 384 (down / up) + tail 3 456
 IMG_BYTES_PER_PIXEL_CHANNEL = 32  # X r/w, y, mask, E[X], E[X^2] r/w (fp32, Philox mode)
 
 
@@ -374,6 +375,45 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
     }
 
 
+def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
+    """BASELINE.json configs[4]: inpainting PSGLA with the DRUNet-architecture denoiser (seeded random init), a batch of
+    independent chains of one 320 x 480 image (a CBSD68 image cropped to multiples of 8) per GPU."""
+    B, H, Wd = args.drunet_chains, args.drunet_h, args.drunet_w
+    K, W = args.drunet_steps, max(args.warmup, 3)
+    s = 5.0 / 255.0  # sampling_images.py:194-198: non-DnCNN denoisers => s = 5/255, delta = s^2; lambda = 25 keeps the
+    lambd = 25.0     # data-term gain (delta/lambda)/sigma^2 at 1 (the script's default lambda = 1 gives 25 and diverges)
+    kw = dict(alpha=1.0, lambd=lambd, sig_float=s, delta=s * s, n_inter=10, n_inter_mmse=10, seed=args.seed)
+    im = synthetic_image(torch, H, Wd, 1, dev)
+    den = P.DRUNet(pretrained=P.random_drunet_state_dict(0), device=dev)
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    run = P.psgla_run(init, dg, den, n_iter=W + K, n_chains=B, chain_id0=rank * B, **kw)
+    for i in range(W):
+        run.step(i)
+    timer = Timer(torch, dev)
+    barrier(torch, P.dist)
+    for i in range(W, W + K):
+        timer.step(lambda: run.step(i))
+    total_ms, per_step = timer.total_ms()
+    barrier(torch, P.dist)
+    total_ms = P.dist.max_over_ranks(total_ms, dev)
+    finite = bool(torch.isfinite(run.X).all().item())
+    px = B * H * Wd
+    tflops = DRUNET_FLOP_PER_PIXEL * px * K / (total_ms * 1e-3) / 1e12
+    return {
+        "metric": "psgla_image_iterations_per_sec_drunet", "unit": "image-iterations/s",
+        "value": B * K * ws / (total_ms * 1e-3), "ms_per_step": total_ms / K, "steps": K, "warmup": W,
+        "config": {"workload": "random inpainting 50%%, sigma=1/255, PSGLA s=5/255 lambda=25 delta=s^2 alpha=1, DRUNet "
+                               "(KAIR UNetRes 64/128/256/512, seeded random-init), %d chains/GPU of %dx%dx3" % (B, H, Wd),
+                   "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
+        "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 69 * K,
+        "roofline": {"kernel": "whole iteration: 1 pre + 68 conv launches (conv_gemm_kernel<128|256>, conv3x3_ts_kernel<64>)",
+                     "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": tflops / peaks["bf16_tflops"],
+                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "traffic": None},
+        "state_finite": finite, "per_step_ms": [round(v, 3) for v in per_step],
+    }
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle)
 def _cpu_chain_worker(job):
     """One host core: the reference's single-chain Python loop (sampling_2D.py:48-72 / :21-45)."""
@@ -513,6 +553,11 @@ def main():
     ap.add_argument("--image-chains", type=int, default=32, help="independent PSGLA chains per GPU")
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--image-steps", type=int, default=20)
+    ap.add_argument("--drunet-chains", type=int, default=64, help="independent DRUNet-PSGLA chains per GPU (configs[4])")
+    ap.add_argument("--drunet-h", type=int, default=320)
+    ap.add_argument("--drunet-w", type=int, default=480)
+    ap.add_argument("--drunet-steps", type=int, default=6)
+    ap.add_argument("--skip-drunet", action="store_true")
     ap.add_argument("--ref-chain-steps", type=int, default=20000, help="--impl reference: steps per core per bench step")
     ap.add_argument("--cpu-sample-steps", type=int, default=100000, help="cpu_baseline sample: steps of one CPU chain")
     ap.add_argument("--skip-image", action="store_true")
@@ -551,9 +596,11 @@ def main():
     if rank == 0:
         sampler.start()
     g = bench_gmm2d(args, P, torch, rank, ws, dev)
-    img = None
+    img = dru = None
     if not args.skip_image:
         img = bench_image(args, P, torch, rank, ws, dev, peaks)
+        if not args.skip_drunet:
+            dru = bench_image_drunet(args, P, torch, rank, ws, dev, peaks)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -582,6 +629,8 @@ def main():
     }
     if img is not None:
         line["image"] = img
+    if dru is not None:
+        line["image_drunet"] = dru
     if ws == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_baseline_gmm2d(args.cpu_sample_steps)
         if img is not None:

@@ -228,6 +228,63 @@ def check_step_series():
     print("clocks:", " | ".join(l.strip() for l in smi.stdout.read().splitlines()[:40]), flush=True)
 
 
+def check_drunet_breakdown():
+    """DRUNet: time per stage (CUDA events) and whole PSGLA iteration, 256x256 (or DIAG_HW=HxW), DIAG_B chains."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    B = int(os.environ.get("DIAG_B", "16"))
+    H, W = [int(v) for v in os.environ.get("DIAG_HW", "256x256").split("x")]
+    dev = torch.device("cuda")
+    den = P.DRUNet(pretrained=P.random_drunet_state_dict(0), device=dev)
+    im = torch.rand(1, 3, H, W, device=dev)
+    dg, init, y, mask = P.make_inpainting(im, 0.5, 1.0, 0)
+    s = 5 / 255
+    run = P.psgla_run(init, dg, den, 1.0, 25.0, s, s * s, n_iter=1000, n_inter=10, n_inter_mmse=10, seed=0, n_chains=B)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    it = [0]
+
+    def step():
+        run.step(it[0])
+        it[0] += 1
+    for _ in range(5):
+        step()
+    t_step = timed(step, 10)
+    flop = 4235136.0 * B * H * W
+    print("DRUNet B=%d %dx%d  PSGLA iteration %.1f us -> %.1f image-it/s, %.1f TFLOP/s" % (B, H, W, t_step, B / t_step * 1e6, flop / t_step / 1e6), flush=True)
+    # individual general layers
+    def layer(mode, h, w, cin, cout, res):
+        wt = torch.zeros(9 * cout * cin, device=dev, dtype=torch.bfloat16)
+        ho, wo = {0: (h, w), 1: (h // 2, w // 2), 2: (2 * h, 2 * w)}[mode]
+        x = torch.zeros(B * h * w * cin, device=dev, dtype=torch.bfloat16)
+        o = torch.zeros(B * ho * wo * cout, device=dev, dtype=torch.bfloat16)
+        r = torch.zeros_like(o) if res else None
+        f = lambda: P._lib.check(lib.psgla_convg_layer(mode, B, h, w, cin, cout, wt.data_ptr(), x.data_ptr(),
+                                                      r.data_ptr() if res else None, None, o.data_ptr(), 0, None), "convg")
+        t = timed(f, 10)
+        taps = {0: 9, 1: 4, 2: 4}[mode]
+        npx = B * (ho * wo if mode != 2 else h * w)
+        fl = 2.0 * taps * cin * cout * npx
+        print("  mode %d %4dx%-4d %3d->%3d res=%d : %7.1f us  %.0f TFLOP/s" % (mode, h, w, cin, cout, res, t, fl / t / 1e6), flush=True)
+    for sc, c in ((1, 128), (2, 256), (3, 512)):
+        layer(0, H >> sc, W >> sc, c, c, 0)
+        layer(0, H >> sc, W >> sc, c, c, 1)
+    for sc, c in ((0, 64), (1, 128), (2, 256)):
+        layer(1, H >> sc, W >> sc, c, 2 * c, 0)
+        layer(2, H >> (sc + 1), W >> (sc + 1), 2 * c, c, 0)
+
+
 def check_mma_rate():
     """Cycles per tcgen05.mma (M128 x N x K16 bf16) for SS / shifted-SS / TS operand sources, one CTA and all SMs."""
     import torch
