@@ -327,6 +327,49 @@ def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000,
     return Xlist, Xlist_mmse, Xlist_mmse2
 
 
+def pnp(init, data_grad, Pb, denoiser, alpha, lambd, sig_float=0.0055, delta=1e-5, n_iter=500, device="cpu"):
+    """restoration_algorithms.py:386-463 (PnP forward-backward): PSGLA without the noise, every iterate stored, the
+    denoiser level held at 40/255 for the first n_iter // 10 iterations of an inpainting problem (:444-447)."""
+    X = init.clone().detach()
+    delta = torch.tensor(delta).to(device).to(torch.float32)
+    sig = torch.tensor(sig_float).to(device).to(torch.float32)
+    Xlist = []
+    with torch.no_grad():
+        for i in range(n_iter):
+            sig_den = 40.0 / 255.0 if (Pb == "inpainting" and i < n_iter // 10) else sig
+            Y = X + (delta / lambd) * data_grad(X)  # :449
+            X = (1 - alpha) * Y + alpha * denoiser.forward(Y, sig_den)  # :451
+            Xlist.append(torch.squeeze(X))
+    return Xlist, [torch.squeeze(X)], []
+
+
+def red(init, data_grad, Pb, denoiser, lambd, sig_float=0.0055, delta=1e-5, n_iter=500, device="cpu"):
+    """restoration_algorithms.py:465-529 (RED): X+ = X + delta grad - delta lambd (X - D(X; sig)); level 50/255 for the
+    first 10 iterations of an inpainting problem (:512-515)."""
+    X = init.clone().detach()
+    delta = torch.tensor(delta).to(device).to(torch.float32)
+    sig = torch.tensor(sig_float).to(device).to(torch.float32)
+    Xlist = []
+    with torch.no_grad():
+        for i in range(n_iter):
+            sig_den = 50.0 / 255.0 if (i < 10 and Pb == "inpainting") else sig
+            X = X + delta * data_grad(X) - delta * lambd * (X - denoiser.forward(X, sig_den))  # :518
+            Xlist.append(torch.squeeze(X))
+    return Xlist, [torch.squeeze(X)], []
+
+
+class SigmaBlendDenoiser:
+    """Test double that makes the noise-level argument observable: D(x, sigma) = x + (1 + 4 sigma) R(x) with R the
+    residual of a (sigma-blind) DnCNN.  Used to pin the sigma-annealing schedules of pnp / red."""
+
+    def __init__(self, dncnn):
+        self.net = dncnn
+
+    def forward(self, x, sigma):
+        s = float(sigma.reshape(-1)[0]) if isinstance(sigma, torch.Tensor) else float(sigma)
+        return x + (1.0 + 4.0 * s) * (self.net(x) - x)
+
+
 def make_prior_grad(denoiser, alpha, s1, s2, device="cpu"):
     """sampling_images.py:155-157."""
     alphat = torch.tensor(alpha, dtype=torch.float32, device=device)

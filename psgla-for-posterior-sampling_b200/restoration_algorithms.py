@@ -27,7 +27,7 @@ from . import _lib
 from .denoisers import DRUNet, DnCNN
 from .operators import DeblurDataGrad, InpaintingDataGrad, PriorGrad
 
-__all__ = ["psgla", "pnpula", "pnp_ula", "psgla_run", "pnpula_run"]
+__all__ = ["psgla", "pnpula", "pnp_ula", "psgla_run", "pnpula_run", "pnp", "red"]
 
 
 def _f(v):
@@ -237,3 +237,43 @@ def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000,
 
 
 pnp_ula = pnpula
+
+
+def pnp(init, data_grad, Pb, denoiser, alpha, lambd, sig_float=0.0055, delta=1e-5, n_iter=500, device=None, path=None,
+        save_images_online=False, name=None, *, n_chains=None):
+    """PnP forward-backward (restoration_algorithms.py:386-463): PSGLA without the noise.  Y = X + (delta/lambd)
+    data_grad(X); X = (1 - alpha) Y + alpha D(Y; sig_den), sig_den = 40/255 for the first n_iter // 10 iterations of an
+    inpainting problem, else sig_float (only DRUNet reads it).  Returns (all iterates, [last iterate], [])."""
+    run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, 1, max(int(n_iter), 1), seed=0,
+                    n_chains=n_chains)
+    run.pre_params.noise_scale = 0.0
+    print("delta = {}, sigma = {}".format(delta, sig_float))
+    sig32 = float(np.float32(sig_float))
+    for i in range(run.n_iter):
+        if not denoiser.is_residual:
+            run.pre_params.den_in_c3 = 40.0 / 255.0 if (Pb == "inpainting" and i < run.n_iter // 10) else sig32
+        run.step(i)
+    return run.Xlist, [run._out(run.X.clone())], []
+
+
+def red(init, data_grad, Pb, denoiser, lambd, sig_float=0.0055, delta=1e-5, n_iter=500, device=None, path=None,
+        save_images_online=False, name=None, *, n_chains=None):
+    """RED (restoration_algorithms.py:465-529): X+ = X + delta data_grad(X) - delta lambd (X - D(X; sig_den)), sig_den =
+    50/255 for the first 10 iterations of an inpainting problem.  Returns (all iterates, [last iterate], [])."""
+    if not isinstance(denoiser, (DnCNN, DRUNet)):
+        raise TypeError("denoiser must be a psgla_b200.DnCNN or psgla_b200.DRUNet")
+    run = _Run(init, data_grad, denoiser, n_iter, 1, max(int(n_iter), 1), 0, None, "philox", n_chains, 0)
+    delta32 = float(np.float32(delta))
+    g = delta32 * _f(lambd)
+    pre = _lib.PreParams()
+    pre.alg = _lib.ALG_PNPULA  # the denoiser sees X; the projection term is switched off
+    pre.gain_data = delta32 / run.dg.sigma2
+    pre.noise_scale, pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0, 0.0
+    pre.x_gain = 0.0 if denoiser.is_residual else -g
+    run.configure(pre, g)
+    print("delta = {}, sigma = {}".format(delta, sig_float))
+    sig32 = float(np.float32(sig_float))
+    for i in range(run.n_iter):
+        pre.den_in_c3 = 0.0 if denoiser.is_residual else (50.0 / 255.0 if (i < 10 and Pb == "inpainting") else sig32)
+        run.step(i)
+    return run.Xlist, [run._out(run.X.clone())], []

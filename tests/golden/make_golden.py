@@ -115,6 +115,15 @@ def images():
                 "ula.noise": noise.numpy(), "ula.X": torch.stack(Xl).numpy(), "ula.M": torch.stack(Xm).numpy(),
                 "ula.M2": torch.stack(Xm2).numpy(),
                 "ula.params": np.array([delta, lam, alpha, s1, s2, n_iter, n_inter, n_mm, 2])})
+    # PnP forward-backward and RED (restoration_algorithms.py:386-529) with a sigma-sensitive test denoiser, so that the
+    # sigma-annealing schedules are pinned too
+    sden = io_.SigmaBlendDenoiser(den)
+    Xl, Xf, _ = ra.pnp(init=inp["init"], data_grad=inp["data_grad"], Pb="inpainting", denoiser=sden, alpha=torch.tensor(0.9),
+                       lambd=torch.tensor(5.0), sig_float=prm["s"], delta=prm["delta"], n_iter=30, device="cpu")
+    out.update({"pnp.X": torch.stack(Xl).numpy(), "pnp.params": np.array([0.9, 5.0, prm["s"], prm["delta"], 30])})
+    Xl, Xf, _ = ra.red(init=inp["init"], data_grad=inp["data_grad"], Pb="inpainting", denoiser=sden, lambd=torch.tensor(2000.0),
+                       sig_float=prm["s"], delta=2e-5, n_iter=14, device="cpu")
+    out.update({"red.X": torch.stack(Xl).numpy(), "red.params": np.array([2000.0, prm["s"], 2e-5, 14])})
     np.savez_compressed(os.path.join(HERE, "image_golden.npz"), **out)
     print("images: psgla", out["psgla.X"].shape, out["psgla.M"].shape, "ula", out["ula.X"].shape, out["ula.M"].shape)
 

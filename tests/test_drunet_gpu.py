@@ -176,3 +176,30 @@ def test_pnpula_drunet_replay_against_oracle(drunets):
     assert len(Xr) == len(Xg) and len(Mr) == len(Mg)
     for a, b in zip(Xr + Mr, Xg + Mg):
         assert (a - b).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("family", ["dncnn", "drunet"])
+def test_pnp_and_red_against_oracle(drunets, family):
+    """The deterministic siblings (restoration_algorithms.py:386-529) reuse the Langevin kernels with the noise switched
+    off; DRUNet makes the sigma-annealing schedules (40/255 for n_iter // 10 iterations, 50/255 for 10) observable."""
+    if family == "drunet":
+        den, net = drunets
+    else:
+        sd = io_.make_dncnn_weights(seed=0, n_power_iter=5, spatial=16)
+        den = P.DnCNN(pretrained=sd)
+        net = io_.DnCNN().cuda()
+        net.load_state_dict(sd)
+    torch.manual_seed(2)
+    im = torch.rand(1, 3, 32, 40, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    s = 5 / 255
+    kw = dict(alpha=torch.tensor(0.8, device="cuda"), lambd=torch.tensor(25.0, device="cuda"), sig_float=s, delta=s * s, n_iter=22)
+    Xr, Fr, _ = io_.pnp(init, dg, "inpainting", net, device="cuda", **kw)
+    Xg, Fg, Eg = P.pnp(init, dg, "inpainting", den, **kw)
+    assert Eg == [] and len(Fg) == 1 and len(Xg) == len(Xr) == 22
+    assert max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)) < 2e-2
+    kw = dict(lambd=torch.tensor(3000.0, device="cuda"), sig_float=s, delta=1e-5, n_iter=14)
+    Xr, Fr, _ = io_.red(init, dg, "inpainting", net, device="cuda", **kw)
+    Xg, Fg, Eg = P.red(init, dg, "inpainting", den, **kw)
+    assert Eg == [] and len(Xg) == 14
+    assert max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)) < 2e-2
