@@ -219,6 +219,7 @@ def bench_gmm2d(args, P, torch, rank, ws, dev):
         timer.step(lambda: ch.run(n_steps))
         flop += FLOP_PER_CHAIN_STEP[CELLS[k % len(CELLS)][2]] * float(n_chains) * n_steps
     total_ms, per_step = timer.total_ms()
+    launches_per_step = int(P._lib.lib().psgla_gmm2d_last_launches())
     barrier(torch, P.dist)
     total_ms = P.dist.max_over_ranks(total_ms, dev)
 
@@ -261,7 +262,8 @@ def bench_gmm2d(args, P, torch, rank, ws, dev):
             w2["%s|%s|y=(%g,%g)" % (alg, prior, y[0], y[1])] = round(P.Wasserstein_distance(sub, ref, rng=rng), 4)
     units = float(n_chains) * n_steps * K * ws
     return dict(value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
-                e2e_value=units / (e2e_ms * 1e-3), e2e_ms=e2e_ms, h2d=n_chains * 2 * 4, d2h=n_chains * 2 * 4, w2=w2)
+                e2e_value=units / (e2e_ms * 1e-3), e2e_ms=e2e_ms, h2d=n_chains * 2 * 4, d2h=n_chains * 2 * 4, w2=w2,
+                launches_per_step=launches_per_step)
 
 
 # ------------------------------------------------------------------------------------------------ image PSGLA (product)
@@ -617,14 +619,15 @@ def main():
         "clocks": clocks,
         "e2e": {"value": g["e2e_value"], "unit": "chain-steps/s", "h2d_bytes_per_step": g["h2d"],
                 "d2h_bytes_per_step": g["d2h"]},
-        "gpu_launches": K,
-        "roofline": {"kernel": "gmm2d_kernel<float,*,true,4> (one launch per step)", "bound": "fp32",
+        "gpu_launches": K * g["launches_per_step"],
+        "roofline": {"kernel": "gmm2d_kernel<float,*,true,{4,3}> (%d occupancy-sized waves per step)" % g["launches_per_step"],
+                     "bound": "fp32",
                      "achieved": achieved_tflops / ws, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                      "frac": achieved_tflops / ws / FP32_PEAK_TFLOPS_NOMINAL,
                      "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure); "
                                     "algorithmic 82/88 flop + 7 MUFU per chain-step, Philox INT work not counted",
                      "mufu_gops": g["value"] / ws * MUFU_PER_CHAIN_STEP / 1e9,
-                     "launch_ms": g["total_ms"] / K, "traffic": None},
+                     "launch_ms": g["total_ms"] / K / g["launches_per_step"], "traffic": None},
         "w2_squared_to_true_posterior": g["w2"],
     }
     if img is not None:

@@ -43,6 +43,9 @@ int psgla_abi_version(void);
 /* sizeof() of the structs below as the library was compiled (0: psgla_gmm2d_problem, 1: psgla_img_shape, 2: psgla_pre_params,
  * 3: psgla_post_params; -1 otherwise) -- lets a binding verify its struct layout. */
 int psgla_struct_size(int which);
+/* Philox4x32-10 (Salmon et al., SC'11) block function as the kernels use it: counter[4], key[2] -> out[4].  Host code,
+ * no GPU needed; the tests pin it to the Random123 known-answer vectors. */
+void psgla_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out);
 /* compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
 int psgla_device_arch(void);
 
@@ -81,6 +84,10 @@ typedef struct psgla_gmm2d_problem {
 int psgla_gmm2d_run(const psgla_gmm2d_problem* problem, int precision, void* x_dev, int64_t n_chains,
                     int64_t chain_id0, int64_t n_steps, int64_t step0, uint64_t seed, const void* noise_dev,
                     void* traj_dev, int64_t thin, void* stream);
+
+/* How many kernel launches the most recent psgla_gmm2d_run issued (the population is cut into occupancy-sized waves:
+ * full waves of 4 chains per thread plus one remainder wave).  Bookkeeping for benchmarks. */
+int psgla_gmm2d_last_launches(void);
 
 /* The denoiser alone on n points (utils_2D.py:219-232, log-sum-exp form): out = D(x, epsilon). */
 int psgla_gmm2d_denoise(const psgla_gmm2d_problem* problem, double epsilon, int precision, const void* x_dev,

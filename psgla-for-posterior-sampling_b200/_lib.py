@@ -54,7 +54,9 @@ SIGNATURES = {
     "psgla_abi_version": (_int, []),
     "psgla_device_arch": (_int, []),
     "psgla_struct_size": (_int, [_int]),
+    "psgla_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "psgla_gmm2d_run": (_int, [C.POINTER(GmmProblem), _int, _vp, _i64, _i64, _i64, _i64, _u64, _vp, _vp, _i64, _vp]),
+    "psgla_gmm2d_last_launches": (_int, []),
     "psgla_gmm2d_denoise": (_int, [C.POINTER(GmmProblem), C.c_double, _int, _vp, _vp, _i64, _vp]),
     "psgla_gmm2d_noise": (_int, [_vp, _i64, _i64, _i64, _i64, _u64, _vp]),
     "psgla_img_pre_inpaint": (_int, [C.POINTER(PreParams), ImgShape, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp, _vp]),

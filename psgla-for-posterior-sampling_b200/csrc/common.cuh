@@ -45,23 +45,15 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
                                                        uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0);
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2);
-#else
-    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
-    const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
-#endif
-    const uint32_t lo0 = 0xD2511F53u * c0;
-    const uint32_t lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0;
-    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    // one 32 x 32 -> 64 bit product per multiplier (IMAD.WIDE.U32 on the device), round keys are compile-time offsets
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)i * 0x9E3779B9u);
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)i * 0xBB67AE85u);
     c0 = n0;
-    c1 = lo1;
+    c1 = (uint32_t)p1;
     c2 = n2;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    c3 = (uint32_t)p0;
   }
 }
 
@@ -71,7 +63,8 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (a + 0.5) / 2^32
   const float u2 = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));  // sqrt(-2 ln u1) = sqrt(-2 ln2 log2 u1)
+  float r;  // sqrt(-2 ln u1) = sqrt(-2 ln2 log2 u1): a single MUFU.SQRT, no range fix-up branches (the argument is >= 0)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;

@@ -42,3 +42,10 @@ extern "C" int psgla_struct_size(int which) {
     default: return -1;
   }
 }
+
+// Philox4x32-10 on the host, the same function the kernels inline: known-answer tests bind this.
+extern "C" void psgla_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out) {
+  uint32_t c0 = counter[0], c1 = counter[1], c2 = counter[2], c3 = counter[3];
+  psgla::philox4x32_10(c0, c1, c2, c3, key[0], key[1]);
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}

@@ -132,10 +132,11 @@ __device__ __forceinline__ void langevin_step(const Gmm2dConsts<T>& c, const Gmm
 // ------------------------------------------------------------------------------------------------ the kernel
 // Chain j of thread g is chain index g + j * (gridDim.x * blockDim.x): every global access is coalesced.
 template <typename T, int ALG, bool R2, int CPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, (sizeof(T) == 4 && R2) ? 8 : 1)
 gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comps_gmem, T* __restrict__ x,
-             long long n_chains, unsigned long long chain_id0, long long n_steps, long long step0,
-             unsigned long long seed, const T* __restrict__ noise, T* __restrict__ traj, long long thin) {
+             long long n_chains, long long chain_lo, long long n_launch, unsigned long long chain_id0, long long n_steps,
+             long long step0, unsigned long long seed, const T* __restrict__ noise, T* __restrict__ traj, long long thin) {
+  // This launch owns chains [chain_lo, chain_lo + n_launch) of the call's n_chains (the stride of noise / traj rows).
   using V2 = typename Vec2<T>::type;
   __shared__ Gmm2dComponents<T> comps_smem;
   const Gmm2dComponents<T>* comps = nullptr;
@@ -153,8 +154,8 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
   bool live[CPT];
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
-    const long long ch = g + j * nthreads;
-    live[j] = ch < n_chains;
+    const long long ch = chain_lo + g + j * nthreads;
+    live[j] = g + j * nthreads < n_launch;
     V2 v = live[j] ? reinterpret_cast<const V2*>(x)[ch] : V2{0, 0};
     x0[j] = v.x;
     x1[j] = v.y;
@@ -168,7 +169,7 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
         keep_in = thin;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const long long ch = g + j * nthreads;
+          const long long ch = chain_lo + g + j * nthreads;
           if (live[j]) reinterpret_cast<V2*>(traj)[row * n_chains + ch] = V2{x0[j], x1[j]};
         }
         ++row;
@@ -181,7 +182,7 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
     for (long long k = 0; k < n_steps; ++k) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        const long long ch = g + j * nthreads;
+        const long long ch = chain_lo + g + j * nthreads;
         if (live[j]) {
           const V2 z = reinterpret_cast<const V2*>(noise)[k * n_chains + ch];
           langevin_step<T, ALG, R2>(c, comps, x0[j], x1[j], z.x, z.y);
@@ -197,7 +198,7 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
       const unsigned long long pair = (unsigned long long)t >> 1;
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
-        philox_normal4(seed, chain_id0 + (unsigned long long)(g + j * nthreads), (uint32_t)pair,
+        philox_normal4(seed, chain_id0 + (unsigned long long)(chain_lo + g + j * nthreads), (uint32_t)pair,
                        (uint32_t)(pair >> 32), z[j][0], z[j][1], z[j][2], z[j][3]);
       if ((t & 1) == 0) {
 #pragma unroll
@@ -215,7 +216,7 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
 
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
-    const long long ch = g + j * nthreads;
+    const long long ch = chain_lo + g + j * nthreads;
     if (live[j]) reinterpret_cast<V2*>(x)[ch] = V2{x0[j], x1[j]};
   }
 }
@@ -389,8 +390,28 @@ static int upload_components(const Gmm2dComponents<T>& k, cudaStream_t st, Gmm2d
   return PSGLA_OK;
 }
 
-// Launch geometry: chains are spread so that every SM holds the same number of resident threads (one wave):
-// threads = min(n_chains / CPT, SMs * 2048) rounded up to whole 128-thread blocks.
+// Launch geometry.  The kernel is issue-bound, so what matters is that every SM holds the same number of warps for
+// the whole launch: the population is cut into full waves of (resident threads) x 4 chains, and the remainder runs as
+// one more wave with 1..4 chains per thread.  (A single launch of 10^6 chains at 4 per thread is 1.65 waves: the second,
+// two-thirds-empty wave costs as much as the first.)
+template <typename T, int ALG, bool R2, int CPT>
+static void launch_wave(const Gmm2dConsts<T>& c, const Gmm2dComponents<T>* kdev, T* x, long long n_chains, long long lo,
+                        long long n_launch, unsigned long long chain_id0, long long n_steps, long long step0,
+                        unsigned long long seed, const T* noise, T* traj, long long thin, cudaStream_t st) {
+  const int block = 128;
+  const long long threads = (n_launch + CPT - 1) / CPT;
+  const unsigned grid = (unsigned)((threads + block - 1) / block);
+  gmm2d_kernel<T, ALG, R2, CPT><<<grid, block, 0, st>>>(c, kdev, x, n_chains, lo, n_launch, chain_id0, n_steps, step0, seed,
+                                                      noise, traj, thin);
+}
+
+// Number of kernel launches launch_run makes for n_chains (full 4-chain waves + one remainder wave).
+static int count_waves(long long n_chains, long long resident) {
+  const long long full = n_chains / (4 * resident);
+  return (int)full + ((n_chains - full * 4 * resident) > 0 ? 1 : 0);
+}
+static int g_last_launches = 0;  // launches of the most recent psgla_gmm2d_run on this thread's behalf (bench bookkeeping)
+
 template <typename T, int ALG, bool R2>
 static int launch_run(const Folded& f, T* x, long long n_chains, unsigned long long chain_id0, long long n_steps,
                       long long step0, unsigned long long seed, const T* noise, T* traj, long long thin,
@@ -403,22 +424,32 @@ static int launch_run(const Folded& f, T* x, long long n_chains, unsigned long l
     int rc = upload_components<T>(k, st, &kdev);
     if (rc) return rc;
   }
-  const int block = 128;
-  const long long resident = (long long)num_sms() * 2048;
-  int cpt = 1;
-  if (n_chains > resident) cpt = 2;
-  if (n_chains > 2 * resident) cpt = 4;
-  const long long threads = (n_chains + cpt - 1) / cpt;
-  const unsigned grid = (unsigned)((threads + block - 1) / block);
-  if (cpt == 1)
-    gmm2d_kernel<T, ALG, R2, 1><<<grid, block, 0, st>>>(c, kdev, x, n_chains, chain_id0, n_steps, step0, seed, noise,
-                                                        traj, thin);
-  else if (cpt == 2)
-    gmm2d_kernel<T, ALG, R2, 2><<<grid, block, 0, st>>>(c, kdev, x, n_chains, chain_id0, n_steps, step0, seed, noise,
-                                                        traj, thin);
-  else
-    gmm2d_kernel<T, ALG, R2, 4><<<grid, block, 0, st>>>(c, kdev, x, n_chains, chain_id0, n_steps, step0, seed, noise,
-                                                        traj, thin);
+  static long long resident = 0;  // threads of the 4-chain kernel one wave holds
+  if (!resident) {
+    int per_sm = 0;
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmm2d_kernel<T, ALG, R2, 4>, 128, 0));
+    resident = (long long)num_sms() * (per_sm > 0 ? per_sm : 8) * 128;
+  }
+  g_last_launches = count_waves(n_chains, resident);
+  long long lo = 0;
+  while (lo < n_chains) {
+    const long long left = n_chains - lo;
+    if (left >= 4 * resident) {
+      launch_wave<T, ALG, R2, 4>(c, kdev, x, n_chains, lo, 4 * resident, chain_id0, n_steps, step0, seed, noise, traj, thin, st);
+      lo += 4 * resident;
+      continue;
+    }
+    const int cpt = (int)((left + resident - 1) / resident);  // 1..4
+    if (cpt <= 1)
+      launch_wave<T, ALG, R2, 1>(c, kdev, x, n_chains, lo, left, chain_id0, n_steps, step0, seed, noise, traj, thin, st);
+    else if (cpt == 2)
+      launch_wave<T, ALG, R2, 2>(c, kdev, x, n_chains, lo, left, chain_id0, n_steps, step0, seed, noise, traj, thin, st);
+    else if (cpt == 3)
+      launch_wave<T, ALG, R2, 3>(c, kdev, x, n_chains, lo, left, chain_id0, n_steps, step0, seed, noise, traj, thin, st);
+    else
+      launch_wave<T, ALG, R2, 4>(c, kdev, x, n_chains, lo, left, chain_id0, n_steps, step0, seed, noise, traj, thin, st);
+    lo = n_chains;
+  }
   PSGLA_CUDA_TRY(cudaGetLastError());
   if (kdev) PSGLA_CUDA_TRY(cudaFreeAsync(kdev, st));
   return PSGLA_OK;
@@ -495,6 +526,8 @@ extern "C" int psgla_gmm2d_denoise(const psgla_gmm2d_problem* problem, double ep
   return precision == 0 ? denoise_impl<float>(problem, f, x_dev, out_dev, n, (cudaStream_t)stream)
                         : denoise_impl<double>(problem, f, x_dev, out_dev, n, (cudaStream_t)stream);
 }
+
+extern "C" int psgla_gmm2d_last_launches(void) { return g_last_launches; }
 
 extern "C" int psgla_gmm2d_noise(float* out_dev, int64_t n_chains, int64_t chain_id0, int64_t n_steps, int64_t step0,
                                  uint64_t seed, void* stream) {
