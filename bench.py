@@ -399,6 +399,28 @@ def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
     barrier(torch, P.dist)
     total_ms = P.dist.max_over_ranks(total_ms, dev)
     finite = bool(torch.isfinite(run.X).all().item())
+    del run
+
+    # ---- e2e: psgla() itself, pinned-host image / mask / observation in, pinned-host posterior mean out
+    n_e2e = 11
+    host = dict(init=init.cpu().pin_memory(), mask=mask.cpu().pin_memory(), y=y.cpu().pin_memory())
+    out_host = torch.empty((B, 3, H, Wd), dtype=torch.float32).pin_memory()
+
+    def e2e_call():
+        with contextlib.redirect_stdout(sys.stderr):
+            dg2 = P.InpaintingDataGrad(host["mask"].to(dev, non_blocking=True), host["y"].to(dev, non_blocking=True), dg.sigma2)
+            Xl, Mm, _ = P.psgla(host["init"].to(dev, non_blocking=True), dg2, den, n_iter=n_e2e, n_chains=B, chain_id0=rank * B, **kw)
+            out_host.copy_(Mm[-1], non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_call()
+    barrier(torch, P.dist)
+    t0 = time.perf_counter()
+    e2e_call()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier(torch, P.dist)
+    e2e_ms = P.dist.max_over_ranks(e2e_ms, dev)
+
     px = B * H * Wd
     tflops = DRUNET_FLOP_PER_PIXEL * px * K / (total_ms * 1e-3) / 1e12
     return {
@@ -408,6 +430,8 @@ def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
                                "(KAIR UNetRes 64/128/256/512, seeded random-init), %d chains/GPU of %dx%dx3" % (B, H, Wd),
                    "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
         "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 69 * K,
+        "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
+                "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
         "roofline": {"kernel": "whole iteration: 1 pre + 68 conv launches (conv_gemm_kernel<128|256>, conv3x3_ts_kernel<64>)",
                      "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": tflops / peaks["bf16_tflops"],
@@ -490,6 +514,34 @@ def cpu_baseline_image(args, n_iter=12):
         dt = time.perf_counter() - t0
     return {"value": n_iter / dt, "unit": "image-iterations/s", "cores": torch.get_num_threads(), "kind": kind,
             "sample": "%d PSGLA iterations, 1 chain, %dx%dx3, fp32 torch DnCNN on the host" % (n_iter, H, H)}
+
+
+def cpu_baseline_drunet(args, n_iter=10):
+    """The reference's psgla loop on the host cores with the fp32 torch DRUNet of the oracle (same weights, same problem)."""
+    import torch
+    import psgla_b200 as P
+    from oracle import image_oracle as io_
+    H, Wd = args.drunet_h, args.drunet_w
+    im = synthetic_image(torch, H, Wd, 1, "cpu")
+    net = io_.DRUNet()
+    net.load_state_dict(P.random_drunet_state_dict(0))
+    net.eval()
+    prob = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0, device="cpu")
+    s = 5.0 / 255.0
+    kw = dict(alpha=torch.tensor(1.0), lambd=torch.tensor(25.0), sig_float=s, delta=s * s, n_inter=10, n_inter_mmse=10, seed=0)
+    kind = "port"
+    if _reference_available():
+        from oracle import ref_loader
+        ra = ref_loader.load_restoration_algorithms()
+        fn, kind = (lambda *a, **k: ra.psgla(*a, device="cpu", **k)), "reference"
+    else:
+        fn = lambda *a, **k: io_.psgla(*a, device="cpu", **k)  # noqa: E731
+    with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")):
+        t0 = time.perf_counter()
+        fn(prob["init"], prob["data_grad"], net, n_iter=n_iter, **kw)
+        dt = time.perf_counter() - t0
+    return {"value": n_iter / dt, "unit": "image-iterations/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d PSGLA iterations, 1 chain, %dx%dx3, fp32 torch DRUNet on the host" % (n_iter, H, Wd)}
 
 
 def run_reference(args):
@@ -641,6 +693,11 @@ def main():
                 img["cpu_baseline"] = cpu_baseline_image(args)
             except Exception as exc:  # noqa: BLE001
                 img["cpu_baseline"] = {"error": repr(exc)[:200]}
+        if dru is not None:
+            try:
+                dru["cpu_baseline"] = cpu_baseline_drunet(args)
+            except Exception as exc:  # noqa: BLE001
+                dru["cpu_baseline"] = {"error": repr(exc)[:200]}
     emit(line)
     if ws > 1:
         import torch.distributed as dist

@@ -27,18 +27,25 @@ using namespace sm100;
 enum { CG_CONV3 = 0, CG_DOWN2 = 1, CG_UP2 = 2 };
 
 constexpr int CG_EPI_WARPS = 8;
-constexpr int CG_THREADS = 64 + 32 * CG_EPI_WARPS;
 constexpr int CG_NACC = 2;
+constexpr int CG_NA = 4;  // TS form: A tiles resident in tensor memory (32 columns each)
 
-template <int N_TILE>
+// TS = true: four loader warps copy every A box from shared memory into tensor memory and the MMAs take A from there
+// (an M128 x N128 x K16 MMA then costs 73 instead of 106 cycles, profiles/r01b_mma_rate.txt); needs N_TILE <= 128 so that
+// two accumulator stages and the A ring fit the 512 TMEM columns.
+template <int N_TILE, bool TS>
 struct CgCfg {
+  static constexpr int THREADS = 64 + (TS ? 128 : 0) + 32 * CG_EPI_WARPS;
+  static constexpr int EPI_WARP0 = TS ? 6 : 2;
+  static constexpr int A_COL0 = CG_NACC * N_TILE;
+  static_assert(!TS || CG_NACC * N_TILE + CG_NA * 32 <= 512, "TS form needs room for the A ring in tensor memory");
   static constexpr int A_BYTES = 128 * 128;     // 128 tile pixels x 64 channels bf16
   static constexpr int B_BYTES = N_TILE * 128;  // N_TILE output channels x 64 input channels bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_COLS = (CG_NACC * N_TILE) < 32 ? 32 : CG_NACC * N_TILE;
+  static constexpr int TMEM_COLS = TS ? 512 : ((CG_NACC * N_TILE) < 32 ? 32 : CG_NACC * N_TILE);
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -92,10 +99,10 @@ __device__ __forceinline__ void cg_add_bf16x8(float (&f)[8], const uint4 r) {
   }
 }
 
-template <int N_TILE>
-__global__ void __launch_bounds__(CG_THREADS, 1)
+template <int N_TILE, bool TS>
+__global__ void __launch_bounds__((CgCfg<N_TILE, TS>::THREADS), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const CgParams p) {
-  using Cfg = CgCfg<N_TILE>;
+  using Cfg = CgCfg<N_TILE, TS>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -103,7 +110,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty = full + NSTAGE;
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + CG_NACC;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty + CG_NACC);
+  uint64_t* afull = tempty + CG_NACC;   // TS: the A box of this k-iteration is in tensor memory
+  uint64_t* aempty = afull + CG_NA;     // TS: the MMAs that read it have completed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(aempty + CG_NA);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +126,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int i = 0; i < CG_NACC; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+    }
+    for (int i = 0; i < CG_NA; ++i) {
+      mbar_init(&afull[i], 4);
+      mbar_init(&aempty[i], 1);
     }
     fence_barrier_init();
   }
@@ -173,25 +186,54 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
       for (int it = 0; it < kiters; ++it, ++L) {
-        const uint32_t slot = L % NSTAGE;
+        const uint32_t slot = L % NSTAGE, as = L % CG_NA;
         mbar_wait(&full[slot], (L / NSTAGE) & 1);
+        if (TS) mbar_wait(&afull[as], (L / CG_NA) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = smem_lo + slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
           const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
+          const uint32_t a_t = tmem_base + Cfg::A_COL0 + as * 32u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc,
-                      (it | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            if (TS)
+              umma_bf16_ts(d_tmem, a_t + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, (it | k) != 0);
+            else
+              umma_bf16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc,
+                        (it | k) != 0);
+          }
           umma_commit(&empty[slot]);
+          if (TS) umma_commit(&aempty[as]);
           if (it == kiters - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
       }
     }
+  } else if (TS && warp < 6) {
+    // ---------------------------------------------------------------- loaders (TS): smem A box -> registers -> TMEM
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t smem_addr = smem_u32(smem);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + Cfg::A_COL0;
+    uint32_t L = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int it = 0; it < kiters; ++it, ++L) {
+        const uint32_t slot = L % NSTAGE, as = L % CG_NA;
+        mbar_wait(&full[slot], (L / NSTAGE) & 1);
+        mbar_wait(&aempty[as], ((L / CG_NA) & 1) ^ 1);
+        tc_fence_after();
+        uint32_t v[32];
+        ld_swizzled_row128(smem_addr + slot * Cfg::STAGE_BYTES, m, v);
+        tmem_st_32x32b_x32(lane_taddr + as * 32u, v);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[as]);
+      }
+    }
   } else {
     // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
-    const int ew = warp - 2;
+    const int ew = warp - Cfg::EPI_WARP0;
     const int grp = ew >> 2;
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;  // tile pixel
@@ -287,18 +329,18 @@ static int cg_cached_map(CUtensorMap* map, const CgMapKey& key, int rank, const 
   return PSGLA_OK;
 }
 
-template <int N_TILE>
+template <int N_TILE, bool TS>
 static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParams& p, cudaStream_t st) {
-  using Cfg = CgCfg<N_TILE>;
+  using Cfg = CgCfg<N_TILE, TS>;
   static bool attr_set = false;
   if (!attr_set) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(CG_THREADS);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -306,7 +348,7 @@ static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParam
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE>, ma, mw, p));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE, TS>, ma, mw, p));
   return PSGLA_OK;
 }
 
@@ -333,7 +375,18 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
   p.ROWS = std::max(1, std::min(128 / p.PX, p.Hg));
   p.tiles_x = (p.Wg + p.PX - 1) / p.PX;
   p.tiles_y = (p.Hg + p.ROWS - 1) / p.ROWS;
-  const int n_tile = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // PSGLA_CG_MODE: 0 (default) = both operands from shared memory with the widest N tile (256 / 128 / 64); 1 = A through
+  // tensor memory with N tiles of 128 / 64.  Measured on B200 (B = 16, 256^2, profiles/r01d_drunet_breakdown.txt): the TS
+  // form is 10-40 % SLOWER here -- every k-iteration's A box is used by only 4 MMAs (292 cycles), less than the
+  // smem -> register -> TMEM latency of one loader pass, so the loaders, not the MMAs, pace the pipeline.  Kept as an
+  // experiment; it needs software-pipelined loaders to pay off.
+  static int cg_mode = -1;
+  if (cg_mode < 0) {
+    const char* e = getenv("PSGLA_CG_MODE");
+    cg_mode = e ? atoi(e) : 0;
+  }
+  const bool ts = cg_mode == 1;
+  const int n_tile = (!ts && Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   p.n_tiles_n = Cout / n_tile;
   p.n_items = B * p.tiles_y * p.tiles_x * p.quads * p.n_tiles_n;
   p.relu = relu;
@@ -363,9 +416,9 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
     rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, Cout, taps_total, n_tile, 0}, 3, dims, strides, box);
   }
   if (rc) return rc;
-  if (n_tile == 256) return cg_launch<256>(ma, mw, p, st);
-  if (n_tile == 128) return cg_launch<128>(ma, mw, p, st);
-  return cg_launch<64>(ma, mw, p, st);
+  if (n_tile == 256) return cg_launch<256, false>(ma, mw, p, st);
+  if (n_tile == 128) return ts ? cg_launch<128, true>(ma, mw, p, st) : cg_launch<128, false>(ma, mw, p, st);
+  return ts ? cg_launch<64, true>(ma, mw, p, st) : cg_launch<64, false>(ma, mw, p, st);
 }
 
 }  // namespace psgla
