@@ -197,6 +197,15 @@ int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, float c3, voi
  * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
 int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
 
+/* PSNR and SSIM of n = shape.B images [n][C][H][W] (fp32) against one reference image [C][H][W], on the device: the
+ * per-sample metric loop of sampling_images.py:373-384 and the MMSE curves of :411-433 without copying samples to the host.
+ * skimage 0.24 definitions as the reference calls them: PSNR = 10 log10(R^2 / MSE); SSIM = 7x7 uniform window, sample
+ * covariance, K1 = 0.01, K2 = 0.03, mean over the interior and the channels (channel_axis=2).  Either output may be NULL.
+ * workspace: psgla_img_metrics_workspace_bytes(n) bytes. */
+size_t psgla_img_metrics_workspace_bytes(int n);
+int psgla_img_psnr_ssim(psgla_img_shape shape, const float* stack_dev, const float* ref_dev, float data_range,
+                        void* workspace_dev, size_t workspace_bytes, float* psnr_out_dev, float* ssim_out_dev, void* stream);
+
 /* DRUNet (deepinv.models.DRUNet(in_channels=3, out_channels=3), sampling_images.py:136; KAIR UNetRes nc = 64/128/256/512,
  * nb = 4, no biases).  weights_host: psgla_drunet_num_weights() = 64 fp32 tensors in state-dict order (m_head, m_down1.*,
  * m_down2.*, m_down3.*, m_body.*, m_up3.*, m_up2.*, m_up1.*, m_tail; torch layouts).  den_in_dev: bf16 NHWC16 as written by a

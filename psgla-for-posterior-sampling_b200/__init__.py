@@ -7,6 +7,8 @@ directory name carries the reference's name and is not a Python identifier).
 """
 from . import _lib  # noqa: F401
 from . import dist  # noqa: F401
+from . import metrics  # noqa: F401
+from .metrics import posterior_summary, psnr_ssim  # noqa: F401
 from .denoisers import (DRUNET_KEYS, DRUNet, DnCNN, lipschitz_dncnn_state_dict, random_dncnn_state_dict,  # noqa: F401
                         random_drunet_state_dict)  # noqa: F401
 from .operators import (DeblurDataGrad, InpaintingDataGrad, PriorGrad, blur_taps, make_deblurring,  # noqa: F401

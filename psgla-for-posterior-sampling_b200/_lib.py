@@ -71,6 +71,8 @@ SIGNATURES = {
                                          _vp, _vp]),
     "psgla_conv3x3_layer": (_int, [_vp, _int, _int, ImgShape, _vp, _vp, _int, _vp]),
     "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, C.c_float, _vp, _vp]),
+    "psgla_img_metrics_workspace_bytes": (_sz, [_int]),
+    "psgla_img_psnr_ssim": (_int, [ImgShape, _vp, _vp, C.c_float, _vp, _sz, _vp, _vp, _vp]),
     "psgla_drunet_num_weights": (_int, []),
     "psgla_drunet_packed_bytes": (_sz, []),
     "psgla_drunet_pack_weights": (_int, [C.POINTER(C.POINTER(C.c_float)), _vp, _vp]),

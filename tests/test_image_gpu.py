@@ -289,3 +289,60 @@ def test_argument_errors(nets):
         P.psgla(init, lambda x: x, den, 1.0, 5.0, n_iter=10, seed=0)
     with pytest.raises(ZeroDivisionError):
         P.psgla(init, dg, den, 1.0, 5.0, n_iter=5, n_inter=1, seed=0, save_images_online=True)
+
+
+@pytest.mark.parametrize("n,H,W", [(1, 7, 7), (5, 37, 50), (3, 256, 256)])
+def test_psnr_ssim_against_oracle(n, H, W):
+    """Device PSNR / SSIM (sampling_images.py:373-384) against the oracle's NumPy restatement of skimage's definitions."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ref = torch.rand(3, H, W, device="cuda", generator=g)
+    imgs = (ref[None] + 0.1 * torch.randn(n, 3, H, W, device="cuda", generator=g)).clamp(0, 1)
+    p, s = P.psnr_ssim(imgs, ref)
+    torch.cuda.synchronize()
+    for i in range(n):
+        a, b = ref.permute(1, 2, 0).cpu().numpy(), imgs[i].permute(1, 2, 0).cpu().numpy()
+        assert abs(p[i].item() - io_.psnr(a, b)) < 1e-3
+        assert abs(s[i].item() - io_.ssim(a, b)) < 2e-4
+    with pytest.raises(RuntimeError, match="7 x 7"):
+        P.psnr_ssim(torch.rand(1, 3, 6, 20, device="cuda"), torch.rand(3, 6, 20, device="cuda"))
+
+
+def test_posterior_summary_matches_reference_formulas(nets):
+    den, net = nets
+    torch.manual_seed(4)
+    im = torch.rand(1, 3, 40, 48, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    s = 2 / 255
+    X, M, M2 = P.psgla(init, dg, den, alpha=1.0, lambd=5.0, sig_float=s, delta=s * s, n_iter=44, n_inter=4, n_inter_mmse=3, seed=1)
+    out = P.posterior_summary(im[0], X, M, M2)
+    imn = im[0].permute(1, 2, 0).cpu().numpy()
+    Mn = np.stack([m.permute(1, 2, 0).cpu().numpy() for m in M])
+    mean_list = np.cumsum(Mn, axis=0) / np.arange(1, len(Mn) + 1)[:, None, None, None]  # sampling_images.py:414
+    want = [io_.psnr(imn, mean_list[i]) for i in range(1, len(Mn))]
+    assert np.allclose(out["psnr_running"].cpu().numpy(), want, atol=1e-3)
+    xm = Mn.mean(0)
+    assert abs(out["psnr_mmse"].item() - io_.psnr(imn, xm)) < 1e-3 and abs(out["ssim_mmse"].item() - io_.ssim(imn, xm)) < 2e-4
+    var = np.stack([m.permute(1, 2, 0).cpu().numpy() for m in M2]).mean(0) - xm ** 2
+    assert np.allclose(out["std"].permute(1, 2, 0).cpu().numpy(), np.sqrt(var * (var >= 0)), atol=1e-4)
+    assert out["psnr_samples"].shape == (len(X),)
+
+
+def test_final_psnr_ssim_parity_long_replay(nets):
+    """North-star parity on the *result*: 300 PSGLA iterations with the reference's own torch.randn stream (rng="torch"),
+    PSNR / SSIM of the MMSE estimate and the per-pixel std map against the fp32 oracle run on the same stream."""
+    den, net = nets
+    torch.manual_seed(8)
+    low = torch.rand(1, 3, 8, 8, device="cuda")
+    im = F.interpolate(low, size=(64, 64), mode="bicubic", align_corners=False).clamp(0, 1)
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("psgla")
+    kw = dict(alpha=torch.tensor(1.0, device="cuda"), lambd=torch.tensor(prm["lambd"], device="cuda"), sig_float=prm["s"],
+              delta=prm["delta"], n_iter=300, n_inter=10, n_inter_mmse=10, seed=21)
+    Xr, Mr, M2r = io_.psgla(init, dg, net, device="cuda", **kw)            # draws torch.randn(generator(seed)) per iteration
+    Xg, Mg, M2g = P.psgla(init, dg, den, rng="torch", **kw)               # same generator, replayed into the kernels
+    a, b = P.posterior_summary(im[0], Xr, Mr, M2r), P.posterior_summary(im[0], Xg, Mg, M2g)
+    assert abs(a["psnr_mmse"].item() - b["psnr_mmse"].item()) < 0.05       # dB
+    assert abs(a["ssim_mmse"].item() - b["ssim_mmse"].item()) < 1e-3
+    assert (a["std"] - b["std"]).abs().max().item() < 5e-3
+    assert (a["psnr_samples"] - b["psnr_samples"]).abs().max().item() < 0.1
+    assert max((u - v).abs().max().item() for u, v in zip(Xr, Xg)) < 2e-2  # per iterate, whole horizon
