@@ -319,6 +319,20 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
     conv_ms, _ = timer.total_ms()
     conv_launch_ms = conv_ms / (reps * 18)
 
+    # ---- the reference's own shape of run: ONE chain (launch-latency bound: 21 launches of ~8 us per iteration)
+    run1 = P.psgla_run(init, dg, den, n_iter=200, n_chains=1, chain_id0=rank, **kw)
+    for i in range(20):
+        run1.step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20, 120):
+        run1.step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    single_chain_its = 100.0 / (e0.elapsed_time(e1) * 1e-3)
+    del run1
+
     # ---- the fused Langevin "pre" kernel alone (HBM-bound stage)
     def pre_only():
         run.pre(W + K - 1, run.pre_params)
@@ -372,6 +386,7 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": pre_gbs / peaks["hbm_gbs"], "launch_ms": pre_launch_ms},
+        "single_chain_iterations_per_sec": single_chain_its,
         "state_finite": finite, "state_absmax": x_absmax,
         "per_step_ms": [round(v, 3) for v in per_step],
     }
