@@ -9,6 +9,8 @@
 // (the denoiser term of either update is added by the last conv layer's epilogue, csrc/conv_tc.cu).
 #include <cuda_bf16.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace psgla {
@@ -119,11 +121,19 @@ constexpr int BT = 32;
 constexpr int MAX_L = 16;
 __constant__ float c_taps[2 * MAX_L + 1];
 
+// i mod n for i in [-n, 2n) by one conditional correction; the general case (tiny images, halo wider than the image)
+// falls back to the remainder.
 __device__ __forceinline__ int wrap(int i, int n) {
-  i %= n;
-  return i < 0 ? i + n : i;
+  if (i < 0) i += n;
+  if (i >= n) i -= n;
+  if (i < 0 || i >= n) {
+    i %= n;
+    if (i < 0) i += n;
+  }
+  return i;
 }
 
+// All loops below are (row = warp, warp + 8, ...; column = lane, lane + 32, ...): no integer division in the hot path.
 template <bool FULL>  // FULL: Langevin pre; else: out = A x
 __global__ void __launch_bounds__(256)
 blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, const float* __restrict__ y, int y_B,
@@ -139,38 +149,42 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
   const int x0 = tx * BT, y0 = ty * BT;
   const long long plane = (long long)H * W;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int prow = tid >> 3, pcol = (tid & 7) * 4;  // this thread's 4 pixels inside the tile
+  const int nt = 2 * l + 1;
+  const int w1 = SW - 2 * l, h1 = SW - 2 * l;  // extent after one pass of A
   float res[3][4];
   float xin[3][4];
 
+#pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float* xp = x + ((long long)b * 3 + c) * plane;
     __syncthreads();
-    for (int i = tid; i < SW * SW; i += 256) {
-      const int r = i / SW, cc = i % SW;
-      s0[i] = xp[(long long)wrap(y0 - halo + r, H) * W + wrap(x0 - halo + cc, W)];
+    for (int r = warp; r < SW; r += 8) {
+      const float* row = xp + (long long)wrap(y0 - halo + r, H) * W;
+      for (int cc = lane; cc < SW; cc += 32) s0[r * SW + cc] = row[wrap(x0 - halo + cc, W)];
     }
     __syncthreads();
-    // horizontal pass of A: s1[r][cc], cc in [0, SW - 2l)  <->  column x0 - halo + l + cc
-    const int w1 = SW - 2 * l;
-    for (int i = tid; i < SW * w1; i += 256) {
-      const int r = i / w1, cc = i % w1;
-      float acc = 0.f;
-      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s0[r * SW + cc + t], acc);
-      s1[r * SW + cc] = acc;
-    }
-    __syncthreads();
-    // vertical pass of A: s0[r][cc], r in [0, SW - 2l)
-    const int h1 = SW - 2 * l;
-    for (int i = tid; i < h1 * w1; i += 256) {
-      const int r = i / w1, cc = i % w1;
-      float acc = 0.f;
-      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s1[(r + t) * SW + cc], acc);
-      if (FULL) {
-        const float* yp = y + ((long long)(y_B > 1 ? b : 0) * 3 + c) * plane;
-        acc -= yp[(long long)wrap(y0 - l + r, H) * W + wrap(x0 - l + cc, W)];
+    // horizontal pass of A: s1[r][cc], cc in [0, w1)  <->  column x0 - halo + l + cc
+    for (int r = warp; r < SW; r += 8)
+      for (int cc = lane; cc < w1; cc += 32) {
+        const float* src = s0 + r * SW + cc;
+        float acc = 0.f;
+        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t], acc);
+        s1[r * SW + cc] = acc;
       }
-      s0[r * SW + cc] = acc;
+    __syncthreads();
+    // vertical pass of A (minus the observation for the Langevin step): s0[r][cc], r in [0, h1)
+    const float* yp = FULL ? y + ((long long)(y_B > 1 ? b : 0) * 3 + c) * plane : nullptr;
+    for (int r = warp; r < h1; r += 8) {
+      const long long yrow = FULL ? (long long)wrap(y0 - l + r, H) * W : 0;
+      for (int cc = lane; cc < w1; cc += 32) {
+        const float* src = s1 + r * SW + cc;
+        float acc = 0.f;
+        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t * SW], acc);
+        if (FULL) acc -= yp[yrow + wrap(x0 - l + cc, W)];
+        s0[r * SW + cc] = acc;
+      }
     }
     __syncthreads();
     if (!FULL) {
@@ -183,19 +197,19 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
       }
       continue;
     }
-    // A^T r: horizontal then vertical on the (BT + 2l)^2 residual in s0
-    const int w2 = w1 - 2 * l;  // == BT
-    for (int i = tid; i < h1 * w2; i += 256) {
-      const int r = i / w2, cc = i % w2;
+    // A^T r: horizontal then vertical on the (BT + 2l)^2 residual in s0 (A^T = A, the taps are symmetric)
+    for (int r = warp; r < h1; r += 8) {
+      const float* src = s0 + r * SW + lane;  // BT == 32 columns: one per lane
       float acc = 0.f;
-      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s0[r * SW + cc + t], acc);
-      s1[r * SW + cc] = acc;
+      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t], acc);
+      s1[r * SW + lane] = acc;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      const float* src = s1 + prow * SW + pcol + j;
       float acc = 0.f;
-      for (int t = 0; t <= 2 * l; ++t) acc = fmaf(c_taps[t], s1[(prow + t) * SW + pcol + j], acc);
+      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t * SW], acc);
       res[c][j] = acc;
     }
   }
@@ -224,6 +238,207 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
     const int gx = x0 + pcol + j;
     if (gx < W)
       store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx) * 16, xin[0][j], xin[1][j], xin[2][j], a.den_in_c3);
+  }
+}
+
+// ---- fast path: even half-width L known at compile time.
+// Profiling showed the stencil is instruction-bound, not bandwidth-bound, so the kernel is written to spend its
+// instructions on FMAs: wrap-around indices are hoisted out of the staging loops, every pass is register-tiled (one task
+// = 4 consecutive outputs along the filtered direction from 4 + 2L staged values: three 16-byte shared-memory loads for
+// 36 FMAs at L = 4), taps sit in registers, tile extents are compile-time, and the result is handed to row-quad owners
+// through shared memory so that one Philox call serves 4 pixels.
+template <bool FULL, int L>
+struct BlurCfg {
+  static constexpr int HALO = FULL ? 2 * L : L;
+  static constexpr int SW = BT + 2 * HALO;  // staged extent of x
+  static constexpr int W1 = SW - 2 * L;     // extent after one pass of A (= BT when !FULL)
+  static constexpr size_t SMEM = (size_t)(2 * SW * SW + (FULL ? W1 * W1 : 0)) * sizeof(float);
+};
+
+template <bool FULL, int L>
+__global__ void __launch_bounds__(256, 3)
+blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const float* __restrict__ y, int y_B,
+              const float* __restrict__ noise, float* __restrict__ out, __nv_bfloat16* __restrict__ den_in) {
+  using Cfg = BlurCfg<FULL, L>;
+  constexpr int HALO = Cfg::HALO, SW = Cfg::SW, W1 = Cfg::W1;
+  constexpr int NT = 2 * L + 1;
+  constexpr int G1 = W1 / 4;  // 4-wide groups per row / per column after the first pass
+  static_assert(L % 2 == 0, "the vectorised passes need an even half-width (W1 % 4 == 0)");
+  static_assert(SW <= 96, "two column iterations per lane cover the staged row only up to 64 + 32");
+  extern __shared__ float sm[];
+  float* s0 = sm;                // [SW][SW]  x with halo, then the residual A x - y, then the result A^T(A x - y)
+  float* s1 = sm + SW * SW;      // [SW][SW]  scratch between the passes
+  float* sy = s1 + SW * SW;      // [W1][W1]  y on the residual's extent
+  const int tiles_x = (W + BT - 1) / BT;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int b = blockIdx.y;
+  const int x0 = tx * BT, y0 = ty * BT;
+  const long long plane = (long long)H * W;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int prow = tid >> 3, pcol = (tid & 7) * 4;  // final owner: row prow, columns pcol..pcol+3 of the tile
+  float h[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) h[t] = c_taps[t];
+  // wrapped global columns of this lane's staged columns (lane, lane + 32, lane + 64)
+  int gxs[3], gys[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gxs[i] = wrap(x0 - HALO + lane + 32 * i, W);
+    gys[i] = wrap(x0 - L + lane + 32 * i, W);
+  }
+  float res[3][4], xc[3][4];
+
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* xp = x + ((long long)b * 3 + c) * plane;
+    __syncthreads();  // previous channel's readers of s0 / s1 are done
+    for (int r = warp; r < SW; r += 8) {
+      const float* row = xp + (long long)wrap(y0 - HALO + r, H) * W;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (lane + 32 * i < SW) s0[r * SW + lane + 32 * i] = row[gxs[i]];
+    }
+    if (FULL) {
+      const float* yp = y + ((long long)(y_B > 1 ? b : 0) * 3 + c) * plane;
+      for (int r = warp; r < W1; r += 8) {
+        const float* row = yp + (long long)wrap(y0 - L + r, H) * W;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (lane + 32 * i < W1) sy[r * W1 + lane + 32 * i] = row[gys[i]];
+      }
+    }
+    __syncthreads();
+    {
+      const float4 v = *reinterpret_cast<const float4*>(s0 + (HALO + prow) * SW + HALO + pcol);  // x at the owned pixels
+      xc[c][0] = v.x, xc[c][1] = v.y, xc[c][2] = v.z, xc[c][3] = v.w;
+    }
+    // horizontal pass of A: s1[r][0..W1)
+    for (int task = tid; task < SW * G1; task += 256) {
+      const int r = task / G1, g = task - r * G1;
+      const float4* src4 = reinterpret_cast<const float4*>(s0 + r * SW + 4 * g);
+      float in[4 + 2 * L];
+#pragma unroll
+      for (int q = 0; q < (4 + 2 * L) / 4; ++q) {
+        const float4 v = src4[q];
+        in[4 * q] = v.x, in[4 * q + 1] = v.y, in[4 * q + 2] = v.z, in[4 * q + 3] = v.w;
+      }
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc = fmaf(h[t], in[k + t], acc);
+        o[k] = acc;
+      }
+      *reinterpret_cast<float4*>(s1 + r * SW + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    if (FULL) {
+      // vertical pass of A minus the observation: residual on W1 x W1 into s0
+      for (int task = tid; task < G1 * W1; task += 256) {
+        const int g = task / W1, cc = task - g * W1;
+        const float* src = s1 + (4 * g) * SW + cc;
+        float in[4 + 2 * L];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * L; ++j) in[j] = src[j * SW];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) acc = fmaf(h[t], in[k + t], acc);
+          s0[(4 * g + k) * SW + cc] = acc - sy[(4 * g + k) * W1 + cc];
+        }
+      }
+      __syncthreads();
+      // A^T (= A): horizontal on W1 rows x BT columns
+      for (int task = tid; task < W1 * (BT / 4); task += 256) {
+        const int r = task / (BT / 4), g = task - r * (BT / 4);
+        const float4* src4 = reinterpret_cast<const float4*>(s0 + r * SW + 4 * g);
+        float in[4 + 2 * L];
+#pragma unroll
+        for (int q = 0; q < (4 + 2 * L) / 4; ++q) {
+          const float4 v = src4[q];
+          in[4 * q] = v.x, in[4 * q + 1] = v.y, in[4 * q + 2] = v.z, in[4 * q + 3] = v.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) acc = fmaf(h[t], in[k + t], acc);
+          o[k] = acc;
+        }
+        *reinterpret_cast<float4*>(s1 + r * SW + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      __syncthreads();
+    }
+    // last vertical pass (column lane, rows 4 warp .. 4 warp + 3), handed to the row-quad owners through s0
+    {
+      const float* src = s1 + (warp * 4) * SW + lane;
+      float in[4 + 2 * L];
+#pragma unroll
+      for (int j = 0; j < 4 + 2 * L; ++j) in[j] = src[j * SW];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc = fmaf(h[t], in[k + t], acc);
+        s0[(warp * 4 + k) * SW + lane] = acc;
+      }
+    }
+    __syncthreads();
+    {
+      const float4 v = *reinterpret_cast<const float4*>(s0 + prow * SW + pcol);
+      res[c][0] = v.x, res[c][1] = v.y, res[c][2] = v.z, res[c][3] = v.w;
+    }
+  }
+
+  const int gy = y0 + prow;
+  if (gy >= H) return;
+  const int gx0 = x0 + pcol;
+  if (gx0 >= W) return;
+  const bool full_quad = gx0 + 3 < W;
+  float xin[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long e0 = (long long)c * plane + (long long)gy * W + gx0;  // element index inside the chain
+    const long long gi0 = (long long)b * 3 * plane + e0;
+    if (!FULL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gx0 + j < W) out[gi0 + j] = res[c][j];
+      continue;
+    }
+    float z[4];
+    if (noise) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = (gx0 + j < W) ? noise[gi0 + j] : 0.f;
+    } else if ((e0 & 3) == 0) {
+      normal_quad(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e0 >> 2), z);  // one call, 4 pixels
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e0 + j));
+    }
+    float bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bv[j] = langevin_base(a, xc[c][j], res[c][j], z[j]);
+      xin[c][j] = (a.alg == PSGLA_ALG_PNPULA) ? xc[c][j] : bv[j];
+    }
+    if (full_quad && (gi0 & 3) == 0) {
+      *reinterpret_cast<float4*>(out + gi0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gx0 + j < W) out[gi0 + j] = bv[j];
+    }
+  }
+  if (FULL) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (gx0 + j < W)
+        store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx0 + j) * 16, xin[0][j], xin[1][j], xin[2][j], a.den_in_c3);
   }
 }
 
@@ -277,9 +492,20 @@ static int check_img(const psgla_img_shape& s) {
   return PSGLA_OK;
 }
 
+// The taps live in constant memory.  A sampler passes the same taps every iteration, so the (stream-ordered) upload is
+// skipped when the host values equal the ones uploaded last on this device by this thread.
 static int upload_taps(const float* h1d_host, int l, cudaStream_t st) {
   PSGLA_REQUIRE(h1d_host != nullptr && l >= 0 && l <= MAX_L, "blur half-width l must be in 0..%d (got %d)", MAX_L, l);
-  PSGLA_CUDA_TRY(cudaMemcpyToSymbolAsync(c_taps, h1d_host, sizeof(float) * (2 * l + 1), 0, cudaMemcpyHostToDevice, st));
+  static thread_local float last[2 * MAX_L + 1];
+  static thread_local int last_l = -1, last_dev = -1;
+  static thread_local cudaStream_t last_stream = nullptr;
+  int dev = 0;
+  PSGLA_CUDA_TRY(cudaGetDevice(&dev));
+  const int n = 2 * l + 1;
+  if (dev == last_dev && l == last_l && st == last_stream && memcmp(last, h1d_host, sizeof(float) * n) == 0) return PSGLA_OK;
+  PSGLA_CUDA_TRY(cudaMemcpyToSymbolAsync(c_taps, h1d_host, sizeof(float) * n, 0, cudaMemcpyHostToDevice, st));
+  memcpy(last, h1d_host, sizeof(float) * n);
+  last_l = l, last_dev = dev, last_stream = st;
   return PSGLA_OK;
 }
 
@@ -314,9 +540,31 @@ extern "C" int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape 
   return PSGLA_OK;
 }
 
+template <bool FULL, int L>
+static int launch_blur_t(const PreArgs& a, psgla_img_shape s, const float* x, const float* y, int y_B, const float* noise,
+                         float* out, void* den_in, cudaStream_t st) {
+  constexpr size_t smem = BlurCfg<FULL, L>::SMEM;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(blur_kernel_t<FULL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles = ((s.W + BT - 1) / BT) * ((s.H + BT - 1) / BT);
+  blur_kernel_t<FULL, L><<<dim3(tiles, s.B), 256, smem, st>>>(a, s.B, s.H, s.W, x, y, y_B, noise, out, (__nv_bfloat16*)den_in);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
 template <bool FULL>
 static int launch_blur(const PreArgs& a, psgla_img_shape s, int l, const float* x, const float* y, int y_B,
                        const float* noise, float* out, void* den_in, cudaStream_t st) {
+  switch (l) {  // compile-time even half-widths (the reference's default is l = 4); anything else takes the generic kernel
+    case 2: return launch_blur_t<FULL, 2>(a, s, x, y, y_B, noise, out, den_in, st);
+    case 4: return launch_blur_t<FULL, 4>(a, s, x, y, y_B, noise, out, den_in, st);
+    case 6: return launch_blur_t<FULL, 6>(a, s, x, y, y_B, noise, out, den_in, st);
+    case 8: return launch_blur_t<FULL, 8>(a, s, x, y, y_B, noise, out, den_in, st);
+    default: break;
+  }
   const int halo = FULL ? 2 * l : l;
   const int SW = BT + 2 * halo;
   const size_t smem = (size_t)2 * SW * SW * sizeof(float);

@@ -285,6 +285,57 @@ def check_drunet_breakdown():
         layer(2, H >> (sc + 1), W >> (sc + 1), 2 * c, c, 0)
 
 
+def check_host_overhead():
+    """Single chain (the reference's shape of run): host enqueue time per iteration vs device time per iteration."""
+    import time
+    import torch
+    import psgla_b200 as P
+    dev = torch.device("cuda")
+    den = P.DnCNN(pretrained=P.random_dncnn_state_dict(0, scale=0.5), device=dev)
+    im = torch.rand(1, 3, 256, 256, device=dev)
+    s = 2 / 255
+    for name, (dg, init) in (("inpaint", P.make_inpainting(im, 0.5, 1.0, 0)[:2]), ("deblur", P.make_deblurring(im, 4, "uniform")[:2])):
+        run = P.psgla_run(init, dg, den, 1.0, 5.0, s, s * s, n_iter=2000, n_inter=10, n_inter_mmse=10, seed=0, n_chains=1)
+        for i in range(30):
+            run.step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(30, 70):  # 40 x 21 launches stay below the driver's launch queue depth: pure host cost
+            run.step(i)
+        t_host = (time.perf_counter() - t0) / 40 * 1e6
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(70, 370):
+            run.step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        print("single chain %-8s host enqueue %.1f us/iteration, device %.1f us/iteration" % (name, t_host, e0.elapsed_time(e1) / 300 * 1e3), flush=True)
+        pre_t = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                run.pre(0, run.pre_params)
+            e1.record()
+            torch.cuda.synchronize()
+            pre_t.append(e0.elapsed_time(e1) / 20 * 1e3)
+        print("   pre kernel alone: %.1f us" % min(pre_t), flush=True)
+    B = 32
+    dg, init, y = P.make_deblurring(im, 4, "uniform")
+    run = P.psgla_run(init, dg, den, 1.0, 5.0, s, s * s, n_iter=100, n_inter=10, n_inter_mmse=10, seed=0, n_chains=B)
+    run.pre(0, run.pre_params)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run.pre(0, run.pre_params)
+    e1.record()
+    torch.cuda.synchronize()
+    print("deblur pre kernel B=32: %.1f us" % (e0.elapsed_time(e1) / 10 * 1e3), flush=True)
+
+
 def check_mma_rate():
     """Cycles per tcgen05.mma (M128 x N x K16 bf16) for SS / shifted-SS / TS operand sources, one CTA and all SMs."""
     import torch
