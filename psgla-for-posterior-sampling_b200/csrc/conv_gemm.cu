@@ -35,8 +35,9 @@ constexpr int CG_NA = 4;  // TS form: A tiles resident in tensor memory (32 colu
 // two accumulator stages and the A ring fit the 512 TMEM columns.
 template <int N_TILE, bool TS>
 struct CgCfg {
-  static constexpr int THREADS = 64 + (TS ? 128 : 0) + 32 * CG_EPI_WARPS;
-  static constexpr int EPI_WARP0 = TS ? 6 : 2;
+  static constexpr int LOADER_WARPS = TS ? 8 : 0;  // two sets of four: set s copies the k-iterations with L % 2 == s
+  static constexpr int THREADS = 64 + 32 * LOADER_WARPS + 32 * CG_EPI_WARPS;
+  static constexpr int EPI_WARP0 = 2 + LOADER_WARPS;
   static constexpr int A_COL0 = CG_NACC * N_TILE;
   static_assert(!TS || CG_NACC * N_TILE + CG_NA * 32 <= 512, "TS form needs room for the A ring in tensor memory");
   static constexpr int A_BYTES = 128 * 128;     // 128 tile pixels x 64 channels bf16
@@ -209,8 +210,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
       }
     }
-  } else if (TS && warp < 6) {
+  } else if (TS && warp < Cfg::EPI_WARP0) {
     // ---------------------------------------------------------------- loaders (TS): smem A box -> registers -> TMEM
+    // One pass (wait, 8 shared-memory loads, tcgen05.st, wait::st, arrive) takes longer than the 4 MMAs of a k-iteration,
+    // so two sets of four warps alternate k-iterations.
+    const int set = (warp - 2) >> 2;
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const uint32_t smem_addr = smem_u32(smem);
@@ -218,6 +222,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t L = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int it = 0; it < kiters; ++it, ++L) {
+        if ((int)(L & 1) != set) continue;
         const uint32_t slot = L % NSTAGE, as = L % CG_NA;
         mbar_wait(&full[slot], (L / NSTAGE) & 1);
         mbar_wait(&aempty[as], ((L / CG_NA) & 1) ^ 1);

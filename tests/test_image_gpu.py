@@ -346,3 +346,41 @@ def test_final_psnr_ssim_parity_long_replay(nets):
     assert (a["std"] - b["std"]).abs().max().item() < 5e-3
     assert (a["psnr_samples"] - b["psnr_samples"]).abs().max().item() < 0.1
     assert max((u - v).abs().max().item() for u, v in zip(Xr, Xg)) < 2e-2  # per iterate, whole horizon
+
+
+def test_reference_edge_behaviours(nets, tmp_path):
+    """Quirks of the reference's samplers that a drop-in must keep (restoration_algorithms.py:123,146-158,211-213,217-218,246)."""
+    den, net = nets
+    torch.manual_seed(0)
+    im = torch.rand(1, 3, 16, 24, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    s = 2 / 255
+    kw = dict(alpha=1.0, lambd=5.0, sig_float=s, delta=s * s)
+    # fewer than 10 iterations run fine without the online-save flag ...
+    X, M, M2 = P.psgla(init, dg, den, n_iter=5, n_inter=2, n_inter_mmse=1, seed=0, **kw)
+    assert len(X) == 3 and len(M) == len(M2) == 2
+    # ... and divide by zero with it (K = int(n_iter / 10) = 0), as in the reference
+    with pytest.raises(ZeroDivisionError):
+        P.psgla(init, dg, den, n_iter=5, n_inter=2, n_inter_mmse=1, seed=0, save_images_online=True, path=str(tmp_path), name="t", **kw)
+    # the online dump: a dict with the reference's keys every n_iter / 10 iterations
+    P.psgla(init, dg, den, n_iter=20, n_inter=5, n_inter_mmse=4, seed=0, save_images_online=True, path=str(tmp_path), name="run", **kw)
+    d = torch.load(str(tmp_path / "run_sampling.pth"))
+    assert set(d) >= {"Samples", "Mmse", "Mmse2", "n_iter", "lambda", "delta"} and d["n_iter"] == 20
+    # n_inter_mmse=None falls back to n_inter (:217-218)
+    Xa, Ma, _ = P.psgla(init, dg, den, n_iter=12, n_inter=3, n_inter_mmse=None, seed=4, **kw)
+    Xb, Mb, _ = P.psgla(init, dg, den, n_iter=12, n_inter=3, n_inter_mmse=3, seed=4, **kw)
+    assert len(Ma) == len(Mb) == 3 and all(torch.equal(a, b) for a, b in zip(Ma, Mb))
+    # a 3-D init is accepted like the reference's squeeze conventions; results are squeezed [3, H, W] tensors
+    Xc, _, _ = P.psgla(init[0], dg, den, n_iter=12, n_inter=3, n_inter_mmse=3, seed=4, **kw)
+    assert Xc[0].shape == (3, 16, 24) and all(torch.equal(a, b) for a, b in zip(Xa, Xc))
+    # no seed: the reference dies with UnboundLocalError at the first randn; here a ValueError up front
+    with pytest.raises(ValueError, match="seed"):
+        P.psgla(init, dg, den, n_iter=12, n_inter=3, **kw)
+    # PnP-ULA keeps the function's own projection box [-1, 2] unless told otherwise (:38; sampling_images.py:358)
+    prm = io_.resolve_params("pnp_ula", s=5.0)
+    pg = P.PriorGrad(den, 1.0, prm["s1"], prm["s2"])
+    big = init + 5.0  # far outside [-1, 2]: the projection term must pull it back
+    Xu, _, _ = P.pnpula(big, dg, pg, torch.tensor(prm["delta"]), torch.tensor(prm["lambd"]), n_iter=12, n_inter=11, seed=0)
+    Xw, _, _ = P.pnpula(big, dg, pg, torch.tensor(prm["delta"]), torch.tensor(prm["lambd"]), n_iter=12, n_inter=11, seed=0,
+                        c_min=-100, c_max=100)
+    assert (Xu[-1] - big[0]).abs().max() > (Xw[-1] - big[0]).abs().max()
