@@ -57,6 +57,34 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
   }
 }
 
+// The ten round keys (k0 + i W0, k1 + i W1) of a seed, computed once on the host and passed as a kernel parameter: in the
+// kernels they are then constant-bank operands of the round's XOR instead of 20 integer adds per Philox call.
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+  PhiloxKeys r;
+  for (int i = 0; i < 10; ++i) {
+    r.k[2 * i] = (uint32_t)seed + (uint32_t)i * 0x9E3779B9u;
+    r.k[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * 0xBB67AE85u;
+  }
+  return r;
+}
+__device__ __forceinline__ void philox4x32_10_keyed(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                    const PhiloxKeys& keys) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ keys.k[2 * i];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ keys.k[2 * i + 1];
+    c0 = n0;
+    c1 = (uint32_t)p1;
+    c2 = n2;
+    c3 = (uint32_t)p0;
+  }
+}
+
 // Two uniform 32-bit words -> two independent N(0,1) (Box-Muller).  u1 in (0,1], theta = 2 pi u2.
 // Fast-math intrinsics on purpose: MUFU.LG2 / MUFU.RSQ-or-SQRT / MUFU.SIN / MUFU.COS; absolute error ~1e-6, far
 // below the Monte-Carlo resolution of any statistic the samplers feed (tests/test_gmm2d_gpu.py checks moments).
@@ -75,6 +103,14 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t subsequen
                                                float& z0, float& z1, float& z2, float& z3) {
   uint32_t c0 = ctr_lo, c1 = ctr_hi, c2 = (uint32_t)subsequence, c3 = (uint32_t)(subsequence >> 32);
   philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller(c0, c1, z0, z1);
+  box_muller(c2, c3, z2, z3);
+}
+
+__device__ __forceinline__ void philox_normal4_keyed(const PhiloxKeys& keys, uint64_t subsequence, uint32_t ctr_lo,
+                                                     uint32_t ctr_hi, float& z0, float& z1, float& z2, float& z3) {
+  uint32_t c0 = ctr_lo, c1 = ctr_hi, c2 = (uint32_t)subsequence, c3 = (uint32_t)(subsequence >> 32);
+  philox4x32_10_keyed(c0, c1, c2, c3, keys);
   box_muller(c0, c1, z0, z1);
   box_muller(c2, c3, z2, z3);
 }

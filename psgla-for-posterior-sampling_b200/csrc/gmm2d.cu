@@ -135,7 +135,7 @@ template <typename T, int ALG, bool R2, int CPT>
 __global__ void __launch_bounds__(128, (sizeof(T) == 4 && R2) ? 8 : 1)
 gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comps_gmem, T* __restrict__ x,
              long long n_chains, long long chain_lo, long long n_launch, unsigned long long chain_id0, long long n_steps,
-             long long step0, unsigned long long seed, const T* __restrict__ noise, T* __restrict__ traj, long long thin) {
+             long long step0, const PhiloxKeys keys, const T* __restrict__ noise, T* __restrict__ traj, long long thin) {
   // This launch owns chains [chain_lo, chain_lo + n_launch) of the call's n_chains (the stride of noise / traj rows).
   using V2 = typename Vec2<T>::type;
   __shared__ Gmm2dComponents<T> comps_smem;
@@ -198,8 +198,8 @@ gmm2d_kernel(const Gmm2dConsts<T> c, const Gmm2dComponents<T>* __restrict__ comp
       const unsigned long long pair = (unsigned long long)t >> 1;
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
-        philox_normal4(seed, chain_id0 + (unsigned long long)(chain_lo + g + j * nthreads), (uint32_t)pair,
-                       (uint32_t)(pair >> 32), z[j][0], z[j][1], z[j][2], z[j][3]);
+        philox_normal4_keyed(keys, chain_id0 + (unsigned long long)(chain_lo + g + j * nthreads), (uint32_t)pair,
+                             (uint32_t)(pair >> 32), z[j][0], z[j][1], z[j][2], z[j][3]);
       if ((t & 1) == 0) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) langevin_step<T, ALG, R2>(c, comps, x0[j], x1[j], T(z[j][0]), T(z[j][1]));
@@ -401,8 +401,8 @@ static void launch_wave(const Gmm2dConsts<T>& c, const Gmm2dComponents<T>* kdev,
   const int block = 128;
   const long long threads = (n_launch + CPT - 1) / CPT;
   const unsigned grid = (unsigned)((threads + block - 1) / block);
-  gmm2d_kernel<T, ALG, R2, CPT><<<grid, block, 0, st>>>(c, kdev, x, n_chains, lo, n_launch, chain_id0, n_steps, step0, seed,
-                                                      noise, traj, thin);
+  gmm2d_kernel<T, ALG, R2, CPT><<<grid, block, 0, st>>>(c, kdev, x, n_chains, lo, n_launch, chain_id0, n_steps, step0,
+                                                      philox_round_keys(seed), noise, traj, thin);
 }
 
 // Number of kernel launches launch_run makes for n_chains (full 4-chain waves + one remainder wave).
