@@ -229,7 +229,8 @@ int psgla_convg_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, cons
 
 /* tcgen05 issue-rate probe (development aid): every one of `grid` CTAs issues iters x 4 MMAs of shape M128 x n x K16
  * (bf16, zeroed operands) back to back and writes the elapsed SM cycles to cycles_dev[block].
- * mode 0: A and B from shared memory; 1: same with the A start address shifted by one 128-byte row; 2: A from TMEM. */
+ * mode 0: A and B from shared memory; 1: same with the A start address shifted by one 128-byte row; 2: A from TMEM;
+ * 3 / 4: as 2 / 0 with consecutive MMAs alternating between two accumulators (n <= 128). */
 int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream);
 
 #if defined(__GNUC__)

@@ -91,8 +91,11 @@ __device__ __forceinline__ void philox4x32_10_keyed(uint32_t& c0, uint32_t& c1, 
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (a + 0.5) / 2^32
   const float u2 = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  float r;  // sqrt(-2 ln u1) = sqrt(-2 ln2 log2 u1): a single MUFU.SQRT, no range fix-up branches (the argument is >= 0)
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
+  // sqrt(-2 ln u1) = sqrt(-2 ln2 log2 u1).  u1 >= 2^-33 is never subnormal and the radicand is >= 0, so the bare MUFU.LG2 /
+  // MUFU.SQRT (.ftz forms) need none of the range fix-ups the library wrappers add.
+  float lg, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;

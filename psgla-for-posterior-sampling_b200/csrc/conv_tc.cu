@@ -1328,7 +1328,8 @@ namespace psgla {
 // One CTA per block issues `iters` x 4 K-steps of M128 x N x K16 bf16 MMAs back to back on zeroed operands and reports
 // the cycles one MMA took.  mode 0: A and B from shared memory (SS); 1: SS with the A start address shifted by one
 // 128-byte row (the conv kernel's dx tap shift); 2: A from tensor memory (TS).
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n, int iters, long long* __restrict__ cycles) {
+template <int mode>  // compile-time so that the issue loop is nothing but the MMAs
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long long* __restrict__ cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sa = smem;                 // 136 rows x 128 B
@@ -1363,6 +1364,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n, int i
         for (int k = 0; k < 4; ++k) {
           if (mode == 2)
             umma_bf16_ts(tbase, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+          else if (mode == 3)  // TS, consecutive MMAs alternate between two accumulators (no back-to-back dependency)
+            umma_bf16_ts(tbase + ((it * 4 + k) & 1) * 128, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+          else if (mode == 4)  // SS, alternating accumulators
+            umma_bf16(tbase + ((it * 4 + k) & 1) * 128, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2),
+                      ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
           else
             umma_bf16(tbase, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
         }
@@ -1385,15 +1391,27 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n, int i
 }  // namespace psgla
 
 extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream) {
-  PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 2 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,
+  PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 4 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,
                 "psgla_selftest_mma_rate: bad argument");
+  PSGLA_REQUIRE(mode < 3 || n <= 128, "alternating-accumulator modes need n <= 128");
   const int smem = 54 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  mma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(mode, n, iters, cycles_dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case 0: mma_rate_kernel<0><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 1: mma_rate_kernel<1><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 2: mma_rate_kernel<2><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 3: mma_rate_kernel<3><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    default: mma_rate_kernel<4><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+  }
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
 }

@@ -342,11 +342,11 @@ def check_mma_rate():
     import psgla_b200 as P
     lib = P._lib.lib()
     iters = 2000
-    for grid in (1, 148):
+    for grid in (148,):
         out = torch.zeros(grid, dtype=torch.int64, device="cuda")
-        for mode, name in ((0, "SS"), (1, "SS+128B"), (2, "TS")):
+        for mode, name in ((0, "SS"), (1, "SS+128B"), (2, "TS"), (3, "TS alt-D"), (4, "SS alt-D")):
             row = []
-            for n in (16, 32, 64, 96, 128, 192, 256):
+            for n in ((16, 32, 64, 96, 128, 192, 256) if mode < 3 else (16, 32, 64, 96, 128)):
                 P._lib.check(lib.psgla_selftest_mma_rate(mode, n, iters, grid, out.data_ptr(), None), "mma_rate")
                 torch.cuda.synchronize()
                 row.append("N=%d: %.1f" % (n, out.double().mean().item() / (iters * 4)))
