@@ -381,7 +381,11 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "roofline": {"kernel": "conv3x3_kernel<64,64,EPI_HIDDEN> (18 of the 21 launches per iteration)", "bound": "tensor",
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
-                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms, "traffic": None},
+                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms,
+                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01e_conv3x3_ts_full.txt): 272.9 MB read +
+                     # 220.4 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2
+                     "traffic": 493.3e6 if (B == 32 and H == 256) else None,
+                     "traffic_source": "profiles/r01e_conv3x3_ts_full.txt"},
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -694,7 +698,11 @@ def main():
                      "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure); "
                                     "algorithmic 82/88 flop + 7 MUFU per chain-step, Philox INT work not counted",
                      "mufu_gops": g["value"] / ws * MUFU_PER_CHAIN_STEP / 1e9,
-                     "launch_ms": g["total_ms"] / K / g["launches_per_step"], "traffic": None},
+                     "launch_ms": g["total_ms"] / K / g["launches_per_step"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01e_gmm2d_full.txt:
+                     # 4.87 MB and 3.17 MB for the two waves of 10^6 chains; the 8 B per chain written back stay in L2)
+                     "traffic": 4.02e6 if (args.chains == 1000000 and g["launches_per_step"] == 2) else None,
+                     "traffic_source": "profiles/r01e_gmm2d_full.txt (mean of the two waves)"},
         "w2_squared_to_true_posterior": g["w2"],
     }
     if img is not None:
