@@ -13,6 +13,7 @@ from .denoisers import (DRUNET_KEYS, DRUNet, DnCNN, lipschitz_dncnn_state_dict, 
                         random_drunet_state_dict)  # noqa: F401
 from .operators import (DeblurDataGrad, InpaintingDataGrad, PriorGrad, blur_taps, make_deblurring,  # noqa: F401
                         make_inpainting)
+from .params import as_pnpula_kwargs, as_psgla_kwargs, sampler_params  # noqa: F401
 from .restoration_algorithms import pnp, pnp_ula, pnpula, pnpula_run, psgla, psgla_run, red  # noqa: F401
 from .sampling_2D import GMMChains, PnP_ULA, SnoPnP_ULA, run_chains  # noqa: F401
 from .utils_2D import (GMMDenoiser, Theorical_MMSE, Wasserstein_distance, constantes_conditionnal_prob,  # noqa: F401

@@ -83,3 +83,23 @@ def test_opaque_callables_are_rejected():
         P.pnpula(torch.zeros(1, 3, 8, 8), lambda x: x, lambda x: x, 1e-6, 1e-6, seed=0)
     with pytest.raises(ValueError):
         P.DeblurDataGrad(np.array([0.2, 0.3, 0.5]), 1, torch.zeros(1, 3, 4, 4), 1.0)  # non-symmetric taps
+
+
+def test_sampler_params_reproduce_the_script_table():
+    """psgla_b200.sampler_params against the oracle's restatement of sampling_images.py:100-123,147-198 (itself pinned by
+    tests/test_oracle_image.py::test_resolve_params_table), including the quirks."""
+    from oracle import image_oracle as io_
+    cases = [("psgla", "DnCNN", {}), ("psgla", "DnCNN", dict(s=4.0, lambd=7.0)), ("psgla", "DRUNet", {}),
+             ("psgla", "DRUNet", dict(s=3.0, lambd=25.0, N=2000)), ("pnp_ula", "DnCNN", {}), ("pnp_ula", "DnCNN", dict(s=5.0)),
+             ("pnp_ula", "DRUNet", dict(N=30000)), ("pnp_ula", "DnCNN", dict(N=100000))]
+    for alg, den, kw in cases:
+        got = P.sampler_params(alg, den=den, **kw)
+        okw = dict(kw)
+        n_given = "N" in okw
+        want = io_.resolve_params(alg, den=den, N=okw.pop("N", 10000), N_given=n_given, **okw)
+        for k in ("s", "lambd", "delta", "N", "n_inter", "n_inter_mmse", "sigma2"):
+            assert got[k] == pytest.approx(want[k], rel=1e-15), (alg, den, kw, k)
+    p = P.sampler_params("pnp_ula")  # the double division by 255 and the thinning computed from the parsed N
+    assert p["s1"] == pytest.approx(2 / 255 / 255) and p["N"] == 100000 and p["n_inter"] == 10 and (p["c_min"], p["c_max"]) == (-1, 2)
+    assert P.sampler_params("psgla", den="DRUNet")["delta"] / P.sampler_params("psgla", den="DRUNet")["lambd"] / (1 / 255) ** 2 == pytest.approx(25.0)
+    assert set(P.as_psgla_kwargs(P.sampler_params("psgla"))) == {"alpha", "lambd", "sig_float", "delta", "seed", "n_iter", "n_inter", "n_inter_mmse"}
