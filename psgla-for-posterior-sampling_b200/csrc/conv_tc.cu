@@ -1335,11 +1335,12 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
   uint8_t* sa = smem;                 // 136 rows x 128 B
   uint8_t* sb = smem + 18 * 1024;     // 256 rows x 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 52 * 1024);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 16);
   for (int i = threadIdx.x; i < 52 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 8, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1359,11 +1360,13 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
     long long t0 = 0, t1 = 0;
     if (elect_one()) {
       t0 = clock64();
-      for (int it = 0; it < iters; ++it) {
+      for (int it = 0; it < (mode >= 5 ? 0 : iters); ++it) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (mode == 2)
             umma_bf16_ts(tbase, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+          else if (mode >= 5)
+            ;  // handled below
           else if (mode == 3)  // TS, consecutive MMAs alternate between two accumulators (no back-to-back dependency)
             umma_bf16_ts(tbase + ((it * 4 + k) & 1) * 128, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
           else if (mode == 4)  // SS, alternating accumulators
@@ -1371,6 +1374,28 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
                       ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
           else
             umma_bf16(tbase, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+        }
+      }
+      if (mode >= 5) {
+        // the conv kernel's issue pattern: per "row" 9 taps x 4 K-steps into one of two accumulators, first MMA overwrites,
+        // B walks the 72 KB weight array (8 KB per tap), A walks a 4-slot ring of 96 columns; one commit per row.
+        // mode 5: commit to a second barrier every row; mode 6: no per-row commit; mode 7: as 5 with A always at slot 0
+        for (int it = 0; it < iters; ++it) {
+          const uint32_t d = tbase + (it & 1) * 64;
+          uint32_t accumulate = 0;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t a_t = tbase + 128 + (mode == 7 ? 0u : (uint32_t)((it + dy) & 3) * 96u);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t bl = b_lo + (uint32_t)((((dy * 3 + dx) * 8192) % 32768 + k * 32) >> 4);
+                umma_bf16_ts(d, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
+                accumulate = 1;
+              }
+          }
+          if (mode != 6) umma_commit(bar + 8);  // a dummy barrier nobody waits on (initialised below)
         }
       }
       umma_commit(bar);
@@ -1391,7 +1416,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
 }  // namespace psgla
 
 extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream) {
-  PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 4 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,
+  PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 7 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,
                 "psgla_selftest_mma_rate: bad argument");
   PSGLA_REQUIRE(mode < 3 || n <= 128, "alternating-accumulator modes need n <= 128");
   const int smem = 54 * 1024;
@@ -1402,6 +1427,9 @@ extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, lon
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -1410,6 +1438,9 @@ extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, lon
     case 1: mma_rate_kernel<1><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
     case 2: mma_rate_kernel<2><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
     case 3: mma_rate_kernel<3><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 5: mma_rate_kernel<5><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 6: mma_rate_kernel<6><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
+    case 7: mma_rate_kernel<7><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
     default: mma_rate_kernel<4><<<grid, 128, smem, st>>>(n, iters, cycles_dev); break;
   }
   PSGLA_CUDA_TRY(cudaGetLastError());

@@ -353,6 +353,21 @@ def check_mma_rate():
             print("mma_rate grid=%d %-8s cycles/MMA  %s" % (grid, name, "  ".join(row)), flush=True)
 
 
+def check_mma_pattern():
+    """The conv kernel's MMA issue pattern alone (no loaders, no epilogue, no TMA): cycles per MMA."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    out = torch.zeros(148, dtype=torch.int64, device="cuda")
+    for mode, name in ((2, "TS same operands"), (5, "conv pattern, commit per row"), (6, "conv pattern, no commits"), (7, "conv pattern, A fixed slot")):
+        for n in (64, 16):
+            iters = 500
+            P._lib.check(lib.psgla_selftest_mma_rate(mode, n, iters, 148, out.data_ptr(), None), "mma_rate")
+            torch.cuda.synchronize()
+            per = out.double().mean().item() / (iters * (4 if mode < 5 else 36))
+            print("mma_pattern %-32s N=%d: %.1f cycles/MMA" % (name, n, per), flush=True)
+
+
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
 
 if __name__ == "__main__":
