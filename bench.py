@@ -389,10 +389,67 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": pre_gbs / peaks["hbm_gbs"], "launch_ms": pre_launch_ms},
+                       "frac": pre_gbs / peaks["hbm_gbs"], "launch_ms": pre_launch_ms,
+                       # the kernel also writes the padded bf16 NHWC16 denoiser input (32 B per pixel), which the algorithmic
+                       # 16 B per pixel-channel above does not count
+                       "moved_gbs_incl_den_in": (16 * 3 + 32) * px / (pre_launch_ms * 1e-3) / 1e9},
         "single_chain_iterations_per_sec": single_chain_its,
         "state_finite": finite, "state_absmax": x_absmax,
         "per_step_ms": [round(v, 3) for v in per_step],
+    }
+
+
+def bench_image_deblur(args, P, torch, rank, ws, dev, peaks):
+    """BASELINE.json configs[3]: uniform 9x9 blur (l = 4), PnP-ULA with DnCNN, a batch of independent chains of one 256 x 256
+    image; hyper-parameters as the script resolves them (sampling_images.py:147-168 via P.sampler_params)."""
+    B, H, Wd = args.image_chains, args.image_size, args.image_size
+    K, W = args.image_steps, max(args.warmup, 3)
+    prm = P.sampler_params("pnp_ula", den="DnCNN")
+    im = synthetic_image(torch, H, Wd, 1, dev)
+    den = P.DnCNN(pretrained=P.lipschitz_dncnn_state_dict(0), device=dev)
+    dg, init, y = P.make_deblurring(im, l=4, blur_type="uniform", sigma=1.0, seed_ip=0)
+    pg = P.PriorGrad(den, prm["alpha"], prm["s1"], prm["s2"])
+    run = P.pnpula_run(init, dg, pg, prm["delta"], prm["lambd"], n_iter=W + K, n_inter=prm["n_inter"],
+                       n_inter_mmse=prm["n_inter_mmse"], seed=args.seed, n_chains=B, chain_id0=rank * B)
+    for i in range(W):
+        run.step(i)
+    timer = Timer(torch, dev)
+    barrier(torch, P.dist)
+    for i in range(W, W + K):
+        timer.step(lambda: run.step(i))
+    total_ms, per_step = timer.total_ms()
+    barrier(torch, P.dist)
+    total_ms = P.dist.max_over_ranks(total_ms, dev)
+    finite = bool(torch.isfinite(run.X).all().item())
+
+    def pre_only():
+        run.pre(W + K - 1, run.pre_params)
+    pre_only()
+    reps = 5
+    for _ in range(reps):
+        timer.step(pre_only)
+    pre_ms, _ = timer.total_ms()
+    pre_launch_ms = pre_ms / reps
+    px = B * H * Wd
+    # blur_kernel_t<true,4>: reads X and y, writes base (fp32, 12 B per pixel-channel) + the bf16 NHWC16 denoiser input (32 B/px)
+    pre_bytes = (12 * 3 + 32) * px
+    step_tflops = DNCNN_FLOP_PER_PIXEL * px * K / (total_ms * 1e-3) / 1e12
+    return {
+        "metric": "pnpula_image_iterations_per_sec_256x256_dncnn_deblur", "unit": "image-iterations/s",
+        "value": B * K * ws / (total_ms * 1e-3), "ms_per_step": total_ms / K, "steps": K, "warmup": W,
+        "config": {"workload": "uniform 9x9 blur (l=4), sigma=1/255, PnP-ULA delta=%.3g lambda=%.3g s1=%.3g (sampling_images.py:147-168), "
+                               "DnCNN depth 20 (seeded random-init, Lipschitz 0.9), %d chains/GPU of %dx%dx3, in-kernel Philox"
+                               % (prm["delta"], prm["lambd"], prm["s1"], B, H, Wd),
+                   "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
+        "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 21 * K,
+        "whole_iteration_tensor_tflops": step_tflops,
+        "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
+        "pre_kernel": {"kernel": "blur_kernel_t<true,4> (A^T(Ax - y) as a shared-memory staged separable circular stencil + "
+                                 "projection + noise)", "bound": "hbm", "achieved": pre_bytes / (pre_launch_ms * 1e-3) / 1e9,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": pre_bytes / (pre_launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": pre_launch_ms,
+                       "algorithmic_bytes_per_pixel": 12 * 3 + 32},
+        "state_finite": finite, "per_step_ms": [round(v, 3) for v in per_step],
     }
 
 
@@ -669,9 +726,10 @@ def main():
     if rank == 0:
         sampler.start()
     g = bench_gmm2d(args, P, torch, rank, ws, dev)
-    img = dru = None
+    img = dru = deb = None
     if not args.skip_image:
         img = bench_image(args, P, torch, rank, ws, dev, peaks)
+        deb = bench_image_deblur(args, P, torch, rank, ws, dev, peaks)
         if not args.skip_drunet:
             dru = bench_image_drunet(args, P, torch, rank, ws, dev, peaks)
     clocks = sampler.stop() if rank == 0 else None
@@ -707,6 +765,8 @@ def main():
     }
     if img is not None:
         line["image"] = img
+    if deb is not None:
+        line["image_deblur"] = deb
     if dru is not None:
         line["image_drunet"] = dru
     if ws == 1 and not args.skip_cpu:

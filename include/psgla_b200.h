@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PSGLA_ABI_VERSION 2
+#define PSGLA_ABI_VERSION 3
 
 enum {
   PSGLA_OK = 0,
@@ -98,6 +98,19 @@ int psgla_gmm2d_denoise(const psgla_gmm2d_problem* problem, double epsilon, int 
 int psgla_gmm2d_noise(float* out_dev, int64_t n_chains, int64_t chain_id0, int64_t n_steps, int64_t step0,
                       uint64_t seed, void* stream);
 
+/* Sliced Wasserstein-2 distance between a chain population and a reference sample of the same size, on the device
+ * (sampling_2D.py:168-170 `ot.sliced.sliced_wasserstein_distance`, and the "metric every k steps" of :38-39,65-66 for a
+ * population resident in HBM): sqrt( mean_p mean_i (sort_i(theta_p . x_i) - sort_i(theta_p . ref_i))^2 ).
+ *   theta_host        [n_proj][2] unit directions (host floats), n_proj <= 128
+ *   ws_dev / ws_bytes caller-owned scratch of psgla_gmm2d_sw2_workspace_bytes(n, n_proj) bytes, 256-byte aligned
+ * psgla_gmm2d_sorted_projections writes the sorted projections [n_proj][n] fp32 (done once for the reference sample);
+ * psgla_gmm2d_sliced_w2 projects + sorts x_dev and writes the distance to *out_dev (a device double; no host sync). */
+size_t psgla_gmm2d_sw2_workspace_bytes(int64_t n, int n_proj);
+int psgla_gmm2d_sorted_projections(const void* x_dev, int precision, int64_t n, const float* theta_host, int n_proj,
+                                   float* out_sorted_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int psgla_gmm2d_sliced_w2(const void* x_dev, int precision, int64_t n, const float* theta_host, int n_proj,
+                          const float* ref_sorted_dev, void* ws_dev, size_t ws_bytes, double* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Image inverse problems.  One "iteration" of psgla (restoration_algorithms.py:232-238) or pnpula (:104-115) on a
  * batch of B independent chains of shape [3][H][W] is
@@ -130,7 +143,29 @@ typedef struct psgla_pre_params {
   uint64_t seed;
   int64_t chain_id0;
   int64_t iteration;
+  /* Which N(0,1) stream the kernel generates when noise_dev is NULL:
+   *   PSGLA_NOISE_PHILOX     the library's own (subsequence = chain_id0 + b, counter = (iteration, element / 4));
+   *   PSGLA_NOISE_TORCH_CUDA the stream of torch.randn((B,3,H,W), generator=Generator("cuda").manual_seed(seed)) -- what
+   *                          the reference draws each iteration (restoration_algorithms.py:104,232) -- bit for bit:
+   *                          torch_offset = the generator's Philox offset before that call and torch_threads = the
+   *                          thread count of torch's launch, both from psgla_torch_cuda_randn_policy(). */
+  int32_t noise_mode;
+  uint32_t torch_threads;
+  uint64_t torch_offset;
 } psgla_pre_params;
+
+enum { PSGLA_NOISE_PHILOX = 0, PSGLA_NOISE_TORCH_CUDA = 1 };
+
+/* Launch policy of torch's CUDA randn for a float tensor of numel elements (ATen DistributionTemplates.h
+ * calc_execution_policy, block 256, unroll 4) on a device with sm_count SMs and max_threads_per_sm resident threads:
+ * *threads = 256 * grid, *offset_step = how far one call advances the generator's Philox offset.  Iteration i of a sampler
+ * that draws once per iteration therefore uses torch_offset = i * offset_step.  Host code, no GPU needed;
+ * sm_count <= 0 asks the current device. */
+int psgla_torch_cuda_randn_policy(int64_t numel, int sm_count, int max_threads_per_sm, uint32_t* threads,
+                                  uint64_t* offset_step);
+/* out_dev[0..numel) = that torch.randn call's values (seed, offset as above).  Test / replay aid. */
+int psgla_img_noise_torch_cuda(int64_t numel, uint64_t seed, uint64_t offset, uint32_t threads, float* out_dev,
+                               void* stream);
 
 int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape shape, const float* x_dev, const float* mask_dev,
                           int mask_B, const float* y_dev, int y_B, const float* noise_dev, float* base_dev,

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpsgla_b200.so")
 
 GMM_MAX_COMPONENTS = 16
 ALG_PSGLA, ALG_PNPULA = 0, 1
+NOISE_PHILOX, NOISE_TORCH_CUDA = 0, 1
 
 
 class GmmProblem(C.Structure):
@@ -38,7 +39,8 @@ class PreParams(C.Structure):
     _fields_ = [("alg", C.c_int32), ("gain_data", C.c_float), ("noise_scale", C.c_float), ("proj_gain", C.c_float),
                 ("c_min", C.c_float), ("c_max", C.c_float), ("x_gain", C.c_float), ("den_in_c3", C.c_float),
                 ("seed", C.c_uint64), ("chain_id0", C.c_int64),
-                ("iteration", C.c_int64)]
+                ("iteration", C.c_int64), ("noise_mode", C.c_int32), ("torch_threads", C.c_uint32),
+                ("torch_offset", C.c_uint64)]
 
 
 class PostParams(C.Structure):
@@ -59,11 +61,16 @@ SIGNATURES = {
     "psgla_gmm2d_last_launches": (_int, []),
     "psgla_gmm2d_denoise": (_int, [C.POINTER(GmmProblem), C.c_double, _int, _vp, _vp, _i64, _vp]),
     "psgla_gmm2d_noise": (_int, [_vp, _i64, _i64, _i64, _i64, _u64, _vp]),
+    "psgla_gmm2d_sw2_workspace_bytes": (_sz, [_i64, _int]),
+    "psgla_gmm2d_sorted_projections": (_int, [_vp, _int, _i64, C.POINTER(C.c_float), _int, _vp, _vp, _sz, _vp]),
+    "psgla_gmm2d_sliced_w2": (_int, [_vp, _int, _i64, C.POINTER(C.c_float), _int, _vp, _vp, _sz, _vp, _vp]),
     "psgla_img_pre_inpaint": (_int, [C.POINTER(PreParams), ImgShape, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp, _vp]),
     "psgla_img_pre_deblur": (_int, [C.POINTER(PreParams), ImgShape, _vp, C.POINTER(C.c_float), _int, _vp, _int, _vp,
                                     _vp, _vp, _vp]),
     "psgla_img_blur": (_int, [ImgShape, _vp, C.POINTER(C.c_float), _int, _vp, _vp]),
     "psgla_img_noise": (_int, [ImgShape, _u64, _i64, _i64, _vp, _vp]),
+    "psgla_torch_cuda_randn_policy": (_int, [_i64, _int, _int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "psgla_img_noise_torch_cuda": (_int, [_i64, _u64, _u64, C.c_uint32, _vp, _vp]),
     "psgla_dncnn_packed_bytes": (_sz, [_int]),
     "psgla_dncnn_pack_weights": (_int, [_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)), _vp, _vp]),
     "psgla_dncnn_workspace_bytes": (_sz, [ImgShape]),

@@ -27,13 +27,56 @@ __device__ __forceinline__ float normal_at(uint64_t seed, uint64_t chain, uint32
   return z[e & 3];
 }
 
+// ---- the stream of torch.randn(shape, generator=torch.Generator("cuda").manual_seed(seed)) (restoration_algorithms.py:
+// 86-87,104 / :212-213,232), reproduced bit for bit so that a seed alone replays the reference's CUDA noise.
+// torch fills a tensor of `numel` floats with a grid-stride kernel of T = 256 * grid threads, each thread owning the Philox
+// subsequence t = its global index, started at the generator's offset (in 32-bit outputs, a multiple of 4); one
+// curand_normal4 per stride serves elements t + T (4 loop + j), j = 0..3.  curand's Box-Muller: u = x 2^-32 + 2^-33,
+// v = y 2^-32 2pi + 2^-33 2pi, s = sqrtf(-2 logf(u)), (s sin v, s cos v) with __sincosf.  Library logf / sqrtf here on
+// purpose (the accurate ones torch is built with); the constants are curand_globals.h's rounded literals.
+__device__ __forceinline__ float torch_cuda_normal_at(uint64_t seed, uint64_t offset, uint32_t T, uint64_t li) {
+  const uint64_t r = li / T;
+  const uint32_t t = (uint32_t)(li - r * T);
+  const uint64_t ctr = (offset >> 2) + (r >> 2);
+  const uint32_t j = (uint32_t)r & 3u;
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = t, c3 = 0;
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t a = j < 2 ? c0 : c2, b = j < 2 ? c1 : c3;
+  const float u = a * 2.3283064e-10f + (2.3283064e-10f / 2);
+  const float v = b * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2);
+  const float s = sqrtf(-2.0f * logf(u));
+  float sn, cs;
+  __sincosf(v, &sn, &cs);
+  return ((j & 1u) ? cs : sn) * s;
+}
+
 struct PreArgs {
   int alg;
   float gain_data, noise_scale, proj_gain, c_min, c_max, x_gain, den_in_c3;
   unsigned long long seed;
   long long chain_id0;
   unsigned int iteration;
+  int noise_mode;              // PSGLA_NOISE_PHILOX or PSGLA_NOISE_TORCH_CUDA
+  unsigned int torch_threads;  // T of the torch launch
+  unsigned long long torch_offset;
+  long long chw;               // elements of one chain (3 H W): global linear index = b chw + e
 };
+
+// The N(0,1) draw of element e of local chain b in the selected stream; `quad` variants serve 4 consecutive elements.
+__device__ __forceinline__ float draw_at(const PreArgs& a, int b, uint32_t e) {
+  if (a.noise_mode == PSGLA_NOISE_TORCH_CUDA)
+    return torch_cuda_normal_at(a.seed, a.torch_offset, a.torch_threads, (uint64_t)b * (uint64_t)a.chw + e);
+  return normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, e);
+}
+__device__ __forceinline__ void draw_quad(const PreArgs& a, int b, uint32_t e0, float (&z)[4]) {  // e0 % 4 == 0
+  if (a.noise_mode == PSGLA_NOISE_TORCH_CUDA) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      z[j] = torch_cuda_normal_at(a.seed, a.torch_offset, a.torch_threads, (uint64_t)b * (uint64_t)a.chw + e0 + j);
+    return;
+  }
+  normal_quad(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, e0 >> 2, z);
+}
 
 __device__ __forceinline__ float langevin_base(const PreArgs& a, float x, float neg_grad_unscaled, float z) {
   // neg_grad_unscaled = mask (x - y)  resp.  A^T(A x - y); the data term is  -gain_data * that.
@@ -86,7 +129,7 @@ pre_inpaint_kernel(PreArgs a, int B, int H, int W, const float* __restrict__ x, 
         zv[0] = t3.x, zv[1 % VEC] = t3.y, zv[2 % VEC] = t3.z, zv[3 % VEC] = t3.w;
       } else {
         float z4[4];
-        normal_quad(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e >> 2), z4);
+        draw_quad(a, b, (uint32_t)e, z4);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) zv[j] = z4[j];
       }
@@ -94,7 +137,7 @@ pre_inpaint_kernel(PreArgs a, int B, int H, int W, const float* __restrict__ x, 
       xv[0] = x[gi];
       mv[0] = mask[mi];
       yv[0] = y[yi];
-      zv[0] = noise ? noise[gi] : normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)e);
+      zv[0] = noise ? noise[gi] : draw_at(a, b, (uint32_t)e);
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) outv[c][j] = langevin_base(a, xv[j], mv[j] * (xv[j] - yv[j]), zv[j]);
@@ -226,8 +269,7 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
       if (gx >= W) continue;
       const float xv = x[rowoff + gx];
       const long long e = (long long)c * plane + (long long)gy * W + gx;
-      const float z = noise ? noise[rowoff + gx]
-                            : normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)e);
+      const float z = noise ? noise[rowoff + gx] : draw_at(a, b, (uint32_t)e);
       const float bv = langevin_base(a, xv, res[c][j], z);
       out[rowoff + gx] = bv;
       xin[c][j] = (a.alg == PSGLA_ALG_PNPULA) ? xv : bv;
@@ -415,10 +457,10 @@ blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const
 #pragma unroll
       for (int j = 0; j < 4; ++j) z[j] = (gx0 + j < W) ? noise[gi0 + j] : 0.f;
     } else if ((e0 & 3) == 0) {
-      normal_quad(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e0 >> 2), z);  // one call, 4 pixels
+      draw_quad(a, b, (uint32_t)e0, z);  // one call, 4 pixels
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) z[j] = normal_at(a.seed, (unsigned long long)(a.chain_id0 + b), a.iteration, (uint32_t)(e0 + j));
+      for (int j = 0; j < 4; ++j) z[j] = draw_at(a, b, (uint32_t)(e0 + j));
     }
     float bv[4];
 #pragma unroll
@@ -458,6 +500,13 @@ noise_kernel(int B, long long chw, unsigned long long seed, long long chain_id0,
 }
 
 __global__ void __launch_bounds__(256)
+noise_torch_cuda_kernel(long long numel, unsigned long long seed, unsigned long long offset, unsigned int T,
+                        float* __restrict__ out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < numel) out[g] = torch_cuda_normal_at(seed, offset, T, (uint64_t)g);
+}
+
+__global__ void __launch_bounds__(256)
 to_nhwc16_kernel(int B, int H, int W, const float* __restrict__ x, float c3, __nv_bfloat16* __restrict__ out) {
   const long long plane = (long long)H * W;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -482,6 +531,16 @@ static int fill_pre(const psgla_pre_params* p, PreArgs* a) {
   a->seed = p->seed;
   a->chain_id0 = p->chain_id0;
   a->iteration = (unsigned int)p->iteration;
+  PSGLA_REQUIRE(p->noise_mode == PSGLA_NOISE_PHILOX || p->noise_mode == PSGLA_NOISE_TORCH_CUDA,
+                "noise_mode=%d is not a PSGLA_NOISE_* value", p->noise_mode);
+  PSGLA_REQUIRE(p->noise_mode != PSGLA_NOISE_TORCH_CUDA || (p->torch_threads >= 256 && p->torch_threads % 256 == 0 &&
+                                                            p->torch_offset % 4 == 0),
+                "PSGLA_NOISE_TORCH_CUDA needs torch_threads (a multiple of 256) and torch_offset (a multiple of 4) from "
+                "psgla_torch_cuda_randn_policy");
+  a->noise_mode = p->noise_mode;
+  a->torch_threads = p->torch_threads;
+  a->torch_offset = p->torch_offset;
+  a->chw = 0;  // set by the caller once the shape is checked
   return PSGLA_OK;
 }
 
@@ -524,6 +583,7 @@ extern "C" int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape 
   PSGLA_REQUIRE(x_dev && mask_dev && y_dev && base_dev && den_in_dev, "psgla_img_pre_inpaint: null pointer");
   PSGLA_REQUIRE((mask_B == 1 || mask_B == s.B) && (y_B == 1 || y_B == s.B), "mask_B / y_B must be 1 or B");
   const long long plane = (long long)s.H * s.W;
+  a.chw = 3 * plane;
   cudaStream_t st = (cudaStream_t)stream;
   if (plane % 4 == 0) {
     const long long n = plane / 4 * s.B;
@@ -591,6 +651,7 @@ extern "C" int psgla_img_pre_deblur(const psgla_pre_params* p, psgla_img_shape s
   PSGLA_REQUIRE(x_dev && y_dev && base_dev && den_in_dev, "psgla_img_pre_deblur: null pointer");
   PSGLA_REQUIRE(x_dev != base_dev, "psgla_img_pre_deblur: base must not alias x (the stencil reads neighbours)");
   PSGLA_REQUIRE(y_B == 1 || y_B == s.B, "y_B must be 1 or B");
+  a.chw = 3LL * s.H * s.W;
   rc = upload_taps(h1d_host, l, (cudaStream_t)stream);
   if (rc) return rc;
   return launch_blur<true>(a, s, l, x_dev, y_dev, y_B, noise_dev, base_dev, den_in_dev, (cudaStream_t)stream);
@@ -616,6 +677,37 @@ extern "C" int psgla_img_noise(psgla_img_shape s, uint64_t seed, int64_t chain_i
   const long long n = (chw + 3) / 4 * s.B;
   noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s.B, chw, seed, chain_id0,
                                                                              (unsigned int)iteration, out_dev);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_torch_cuda_randn_policy(int64_t numel, int sm_count, int max_threads_per_sm, uint32_t* threads,
+                                             uint64_t* offset_step) {
+  PSGLA_REQUIRE(numel > 0 && threads && offset_step, "psgla_torch_cuda_randn_policy: bad argument");
+  if (sm_count <= 0) {
+    int dev = 0;
+    PSGLA_CUDA_TRY(cudaGetDevice(&dev));
+    PSGLA_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    PSGLA_CUDA_TRY(cudaDeviceGetAttribute(&max_threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+  }
+  PSGLA_REQUIRE(max_threads_per_sm >= 256, "max_threads_per_sm must be >= 256");
+  // ATen/native/cuda/DistributionTemplates.h calc_execution_policy: block 256, unroll 4 (one curand_normal4 per stride)
+  const uint64_t block = 256, unroll = 4;
+  uint64_t grid = ((uint64_t)numel + block - 1) / block;
+  const uint64_t cap = (uint64_t)sm_count * (uint64_t)(max_threads_per_sm / 256);
+  if (grid > cap) grid = cap;
+  PSGLA_REQUIRE(grid * block < (1ull << 32), "launch too large");
+  *threads = (uint32_t)(grid * block);
+  *offset_step = (((uint64_t)numel - 1) / (block * grid * unroll) + 1) * 4;
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_img_noise_torch_cuda(int64_t numel, uint64_t seed, uint64_t offset, uint32_t threads, float* out_dev,
+                                          void* stream) {
+  PSGLA_REQUIRE(out_dev && numel > 0 && threads >= 256 && threads % 256 == 0 && offset % 4 == 0,
+                "psgla_img_noise_torch_cuda: bad argument");
+  noise_torch_cuda_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(numel, seed, offset, threads,
+                                                                                            out_dev);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
 }

@@ -6,9 +6,10 @@ tensors.  Per iteration the host issues two C-ABI calls: the fused Langevin "pre
 whose last layer's epilogue applies the denoiser term, thins samples and updates the running moments.
 Extra keyword-only arguments:
   noise          tensor (n_iter, *init.shape) of N(0,1) draws to replay (e.g. the reference's torch.randn stream)
-  rng            "philox" (default: in-kernel Philox4x32-10, keyed by seed / chain id / iteration) or "torch"
+  rng            "philox" (default: in-kernel Philox4x32-10, keyed by seed / chain id / iteration), "torch"
                  (draw ``torch.randn(im_shape, generator=Generator(device).manual_seed(seed))`` per iteration exactly
-                 like the reference and replay it)
+                 like the reference and replay it) or "torch_cuda" (the same stream as "torch" on a CUDA device, generated
+                 bit for bit inside the fused kernel from the seed alone: no randn launch, no noise tensor)
   n_chains       run that many independent chains of the same problem (init broadcast); outputs gain a leading
                  chain axis
   chain_id0      global id of the first chain (Philox subsequence) when chains are sharded over GPUs
@@ -78,11 +79,22 @@ class _Run:
         self.chain_id0 = int(chain_id0)
         self.noise = noise
         self.gen = None
+        self.torch_threads = self.torch_step = 0
         if noise is None and rng == "torch":
             self.gen = torch.Generator(device=self.device)
             self.gen.manual_seed(self.seed)
+        elif noise is None and rng == "torch_cuda":
+            # torch's launch policy for a randn of X.numel() floats on this device (restoration_algorithms.py:104,232 draw
+            # one such tensor per iteration from a private generator, so iteration i starts at offset i * step)
+            props = torch.cuda.get_device_properties(self.device)
+            threads, step = C.c_uint32(), C.c_uint64()
+            _lib.check(_lib.lib().psgla_torch_cuda_randn_policy(self.X.numel(), props.multi_processor_count,
+                                                                props.max_threads_per_multi_processor,
+                                                                C.byref(threads), C.byref(step)),
+                       "psgla_torch_cuda_randn_policy")
+            self.torch_threads, self.torch_step = threads.value, step.value
         elif noise is None and rng != "philox":
-            raise ValueError("rng must be 'philox' or 'torch'")
+            raise ValueError("rng must be 'philox', 'torch' or 'torch_cuda'")
         if noise is not None and tuple(noise.shape[1:]) != tuple(self.X.shape) and not (
                 self.X.shape[0] == 1 and tuple(noise.shape[1:]) == tuple(self.X.shape[1:])):
             raise ValueError("noise must have shape (n_iter, *init.shape)")
@@ -114,6 +126,10 @@ class _Run:
     def pre(self, i, pre: "_lib.PreParams"):
         z = self.z_for(i)
         pre.seed, pre.chain_id0, pre.iteration = self.seed, self.chain_id0, i
+        if self.torch_threads:
+            pre.noise_mode, pre.torch_threads, pre.torch_offset = _lib.NOISE_TORCH_CUDA, self.torch_threads, i * self.torch_step
+        else:
+            pre.noise_mode = _lib.NOISE_PHILOX
         lib = _lib.lib()
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)

@@ -10,6 +10,8 @@ Same positional arguments and return values as the reference.  Extra keyword-onl
   n_chains         run that many independent chains from x_0 (or from a (n_chains, 2) x_0).
   return_trajectory  False -> only the final states, shape (n_chains, 2); True -> reference layout (N, 2) or,
                    with chains, (N // thin..., n_chains, 2).
+  compute_metric_each_step with n_chains: returns (final states, [sliced W2 of the population vs
+                   Sample_posterior[:n_chains] after steps 1, 101, 201, ...]), evaluated on the device.
   seed, chain_id0, philox_offset   Philox key, global id of the first chain, global index of the first step.
   dtype            "float64" (default for one chain: matches the float64 reference to ~1e-12 under replay) or
                    "float32" (throughput path; default when n_chains is given).
@@ -94,6 +96,64 @@ class GMMChains:
         self.step += n_steps
         return traj
 
+    # ---- population metric on the device (sampling_2D.py:38-39,65-66,168-170)
+    def set_reference_sample(self, sample, n_projections=50, seed=0):
+        """Fix the posterior sample ``(n_chains, 2)`` (e.g. ``sample_posterior(...)``) the population is compared with:
+        draws the unit directions like ``utils_2D.sliced_wasserstein_distance`` and sorts the sample's projections once."""
+        torch = self.torch
+        rng = np.random.default_rng(seed)
+        theta = rng.standard_normal((2, int(n_projections)))
+        theta /= np.linalg.norm(theta, axis=0, keepdims=True)
+        self._theta = np.ascontiguousarray(theta.T, dtype=np.float32)  # [P][2]
+        self._theta_c = self._theta.ctypes.data_as(C.POINTER(C.c_float))
+        P = self._theta.shape[0]
+        lib = _lib.lib()
+        nbytes = lib.psgla_gmm2d_sw2_workspace_bytes(self.n_chains, P)
+        if nbytes == 0:
+            raise ValueError("n_projections must be in 1..128")
+        ref = torch.as_tensor(np.asarray(sample) if not isinstance(sample, torch.Tensor) else sample)
+        if tuple(ref.shape) != (self.n_chains, 2):
+            raise ValueError("the reference sample must have shape (n_chains, 2) = (%d, 2)" % self.n_chains)
+        ref = ref.to(self.device, torch.float32).contiguous()
+        self._sw_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._ref_sorted = torch.empty((P, self.n_chains), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.psgla_gmm2d_sorted_projections(_lib.ptr(ref), 0, self.n_chains, self._theta_c, P,
+                                                    _lib.ptr(self._ref_sorted), _lib.ptr(self._sw_ws), nbytes,
+                                                    _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_gmm2d_sorted_projections")
+
+    def sliced_w2(self, out=None):
+        """Sliced W2 between the current population and the reference sample; returns a 0-dim CUDA float64 tensor (or
+        fills ``out``) without synchronising the host."""
+        if getattr(self, "_ref_sorted", None) is None:
+            raise RuntimeError("call set_reference_sample(sample) first")
+        torch = self.torch
+        if out is None:
+            out = torch.empty((), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().psgla_gmm2d_sliced_w2(_lib.ptr(self.state), self.precision, self.n_chains, self._theta_c,
+                                                  self._theta.shape[0], _lib.ptr(self._ref_sorted), _lib.ptr(self._sw_ws),
+                                                  self._sw_ws.numel(), out.data_ptr(), _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_gmm2d_sliced_w2")
+        return out
+
+    def run_with_metric(self, n_steps, every=100):
+        """Advance by n_steps, evaluating the sliced W2 of the population after global steps 1, every+1, 2*every+1, ...
+        (the cadence of sampling_2D.py:38,65: ``i % 100 == 0`` after step i).  Returns a CUDA float64 tensor of the
+        values; the host never waits inside the loop."""
+        n_steps, every = int(n_steps), int(every)
+        marks = [t for t in range(n_steps) if t % every == 0]
+        vals = self.torch.empty(len(marks), dtype=self.torch.float64, device=self.device)
+        done = 0
+        for k, t in enumerate(marks):
+            self.run(t + 1 - done)
+            done = t + 1
+            self.sliced_w2(out=vals[k])
+        if done < n_steps:
+            self.run(n_steps - done)
+        return vals
+
 
 def run_chains(alg, n_steps, y, delta, A, sigma, denoiser, alpha, epsilon=1.0, n_chains=1, x0=None, seed=0,
                chain_id0=0, dtype="float32", device=None, noise=None, thin=0, philox_offset=0):
@@ -123,9 +183,15 @@ def _sampler(alg, N, x_0, y, delta, A, sigma, denoiser, alpha, epsilon, Sample_p
         return np.random.randn(k, 2).reshape(k, 1, 2)
 
     x0_host = chains.state.cpu().numpy().astype(np.float64)
+    if compute_metric_each_step and not single:
+        # a population instead of one trajectory: sliced W2 between the current population and Sample_posterior[:n_chains]
+        # at the reference's cadence, computed where the chains live (no per-evaluation D2H)
+        if noise is not None or rng != "philox":
+            raise ValueError("the population metric runs with rng='philox'")
+        chains.set_reference_sample(np.asarray(Sample_posterior, dtype=np.float64)[:nc])
+        vals = chains.run_with_metric(n_steps, every=100)
+        return chains.state.cpu().numpy().astype(np.float64), [float(v) for v in vals.cpu().numpy()]
     if compute_metric_each_step:
-        if not single:
-            raise ValueError("compute_metric_each_step follows the reference and needs a single chain")
         # Same interleaving of RNG use as the reference: the metric (which permutes with the global stream) runs
         # after steps 0, 100, 200, ... (sampling_2D.py:38-39,65-66).
         rows, W, done = [x0_host], [], 0

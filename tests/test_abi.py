@@ -32,14 +32,14 @@ def test_library_exports_every_symbol(built):
     handle = ctypes.CDLL(built._lib.LIB_PATH)
     for fn in _header_functions():
         assert hasattr(handle, fn), fn
-    assert handle.psgla_abi_version() == 2
+    assert handle.psgla_abi_version() == 3
 
 
 def test_struct_sizes_match_header(built):
     L = built._lib
     assert ctypes.sizeof(L.GmmProblem) == 8 + 4 * 8 + 4 * 8 + 2 * 8 + 16 * (2 + 4 + 1) * 8
     assert ctypes.sizeof(L.ImgShape) == 16
-    assert ctypes.sizeof(L.PreParams) == 56
+    assert ctypes.sizeof(L.PreParams) == 72
     assert ctypes.sizeof(L.PostParams) == 16
     for which, struct in enumerate((L.GmmProblem, L.ImgShape, L.PreParams, L.PostParams)):  # as compiled into the .so
         assert L.lib().psgla_struct_size(which) == ctypes.sizeof(struct)

@@ -103,3 +103,17 @@ def test_sampler_params_reproduce_the_script_table():
     assert p["s1"] == pytest.approx(2 / 255 / 255) and p["N"] == 100000 and p["n_inter"] == 10 and (p["c_min"], p["c_max"]) == (-1, 2)
     assert P.sampler_params("psgla", den="DRUNet")["delta"] / P.sampler_params("psgla", den="DRUNet")["lambd"] / (1 / 255) ** 2 == pytest.approx(25.0)
     assert set(P.as_psgla_kwargs(P.sampler_params("psgla"))) == {"alpha", "lambd", "sig_float", "delta", "seed", "n_iter", "n_inter", "n_inter_mmse"}
+
+
+def test_torch_cuda_randn_policy_arithmetic():
+    """psgla_torch_cuda_randn_policy restates ATen's calc_execution_policy (block 256, unroll 4, grid capped at
+    SMs x resident blocks); host code, checked here against hand-computed cases for a 148-SM / 2048-thread device."""
+    import ctypes as C
+    lib = P._lib.lib()
+    t, s = C.c_uint32(), C.c_uint64()
+    cases = {1: (256, 4), 256: (256, 4), 257: (512, 4), 3 * 256 * 256: (196608, 4), 148 * 8 * 256: (303104, 4),
+             148 * 8 * 256 * 4: (303104, 4), 148 * 8 * 256 * 4 + 1: (303104, 8), 32 * 3 * 256 * 256: (303104, 24)}
+    for numel, want in cases.items():
+        assert lib.psgla_torch_cuda_randn_policy(numel, 148, 2048, C.byref(t), C.byref(s)) == 0
+        assert (t.value, s.value) == want, numel
+    assert lib.psgla_torch_cuda_randn_policy(0, 148, 2048, C.byref(t), C.byref(s)) == -1
