@@ -231,6 +231,9 @@ int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, float c3, voi
  * mode 1: same with a base-offset field (kept for reference, wrong on sm_100a); mode 2: A copied to tensor memory.
  * a_dev: bf16 [136][64], b_dev: bf16 [64][64] (N x K), d_dev: fp32 [128][64]. */
 int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* d_dev, int row_shift, int mode, void* stream);
+/* CTA-pair (cta_group::2) self-test: D[256][64] = A[256][64] B[64][64]^T by one pair of CTAs, A rows split 128 / 128 over
+ * the two CTAs' tensor memories (mode 0) or shared memories (mode 1), B rows split 32 / 32 over their shared memories. */
+int psgla_selftest_umma2(const void* a_dev, const void* b_dev, float* d_dev, int mode, void* stream);
 
 /* PSNR and SSIM of n = shape.B images [n][C][H][W] (fp32) against one reference image [C][H][W], on the device: the
  * per-sample metric loop of sampling_images.py:373-384 and the MMSE curves of :411-433 without copying samples to the host.

@@ -1323,6 +1323,126 @@ extern "C" int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* 
   return PSGLA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair self-test
+// D[256 x 64] = A[256 x 64] B[64 x 64]^T with one cta_group::2 MMA chain: CTA r of the pair holds A rows [128 r, 128 r + 128)
+// in tensor memory (copied there by its own threads) and B rows [32 r, 32 r + 32) in shared memory; the leader issues,
+// both read their 128 accumulator lanes back.  Pins down the operand split, the multicast commit and the remote arrive
+// the conv kernel relies on.  mode 0: A from TMEM (TS); mode 1: A from shared memory (SS).
+namespace psgla {
+__global__ void __launch_bounds__(128, 1)
+selftest_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      float* __restrict__ d, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;                // 128 rows x 128 B
+  uint8_t* sb = smem + 16 * 1024;    // 32 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 20 * 1024);  // 0: TMA landed, 1: MMAs done, 2 (leader): operands ready
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 2);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tptr, 128);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar[0], 128 * 128 + 32 * 128);
+    tma_load_2d(sa, &map_a, &bar[0], 0, (int)rank * 128);
+    tma_load_2d(sb, &map_b, &bar[0], 0, (int)rank * 32);
+  }
+  mbar_wait(&bar[0], 0);
+  if (mode == 0) {
+    uint32_t v[32];
+    ld_swizzled_row128(smem_u32(sa), (int)threadIdx.x, v);
+    tmem_st_32x32b_x32(tbase + ((uint32_t)(warp * 32) << 16) + 64, v);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bar[2]), 0));  // this CTA's operands are in place
+  if (rank == 0 && warp == 0) {
+    mbar_wait_cluster(&bar[2], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, 64);
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t bd = make_smem_desc(smem_u32(sb) + k * 32, 1024, LAYOUT_SW128, 0);
+        if (mode == 0)
+          umma_bf16_ts2(tbase, tbase + 64 + k * 8, bd, idesc, k > 0);
+        else
+          umma_bf16_ss2(tbase, make_smem_desc(smem_u32(sa) + k * 32, 1024, LAYOUT_SW128, 0), bd, idesc, k > 0);
+      }
+      umma_commit2(&bar[1], 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar[1], 0);
+  tc_fence_after();
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tbase + ((uint32_t)(warp * 32) << 16) + half * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j)
+      d[(size_t)(rank * 128 + warp * 32 + lane) * 64 + half * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tbase, 128);
+  }
+}
+}  // namespace psgla
+
+extern "C" int psgla_selftest_umma2(const void* a_dev, const void* b_dev, float* d_dev, int mode, void* stream) {
+  PSGLA_REQUIRE(a_dev && b_dev && d_dev && (mode == 0 || mode == 1), "psgla_selftest_umma2: bad argument");
+  PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return set_error(PSGLA_E_NODEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  CUtensorMap ma, mb;
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint64_t strides[1] = {128};
+  {
+    const cuuint64_t dims[2] = {64, 256};
+    const cuuint32_t box[2] = {64, 128};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a_dev), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PSGLA_E_BADARG, "tensor map A: CUresult %d", (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {64, 64};
+    const cuuint32_t box[2] = {64, 32};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b_dev), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PSGLA_E_BADARG, "tensor map B: CUresult %d", (int)r);
+  }
+  const int smem = 22 * 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, selftest_umma2_kernel, ma, mb, d_dev, mode));
+  return PSGLA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ MMA rate probe
 namespace psgla {
 // One CTA per block issues `iters` x 4 K-steps of M128 x N x K16 bf16 MMAs back to back on zeroed operands and reports

@@ -368,6 +368,29 @@ def check_mma_pattern():
             print("mma_pattern %-32s N=%d: %.1f cycles/MMA" % (name, n, per), flush=True)
 
 
+def check_umma2():
+    """cta_group::2 self-test: D[256 x 64] = A B^T by a CTA pair."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    torch.manual_seed(0)
+    a = torch.randn(256, 64, device="cuda").to(torch.bfloat16).contiguous()
+    b = torch.randn(64, 64, device="cuda").to(torch.bfloat16).contiguous()
+    ref = a.float() @ b.float().t()
+    for mode in (1, 0):
+        d = torch.full((256, 64), float("nan"), device="cuda")
+        P._lib.check(lib.psgla_selftest_umma2(a.data_ptr(), b.data_ptr(), d.data_ptr(), mode, None), "selftest2")
+        torch.cuda.synchronize()
+        err = (d - ref).abs()
+        print("umma2 mode %d: max err %.3g (rows 0-127: %.3g, rows 128-255: %.3g; cols 0-31: %.3g, cols 32-63: %.3g)"
+              % (mode, err.max().item(), err[:128].max().item(), err[128:].max().item(), err[:, :32].max().item(),
+                 err[:, 32:].max().item()), flush=True)
+        if err.max().item() > 1e-3:
+            # which B rows did each column block see?  compare against the swapped halves
+            swapped = a.float() @ torch.cat([b[32:], b[:32]]).float().t()
+            print("   vs swapped B halves: %.3g" % (d - swapped).abs().max().item(), flush=True)
+
+
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
 
 if __name__ == "__main__":
