@@ -270,6 +270,9 @@ int psgla_convg_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, cons
  * mode 0: A and B from shared memory; 1: same with the A start address shifted by one 128-byte row; 2: A from TMEM;
  * 3 / 4: as 2 / 0 with consecutive MMAs alternating between two accumulators (n <= 128). */
 int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream);
+/* The same for a CTA pair: M256 x n x K16 MMAs (cta_group::2), mode 0: A from tensor memory, 1: from shared memory;
+ * cycles_dev[n_pairs] = cycles the leader of each pair took for iters x 4 MMAs. */
+int psgla_selftest_mma_rate2(int mode, int n, int iters, int n_pairs, long long* cycles_dev, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

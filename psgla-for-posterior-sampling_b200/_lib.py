@@ -89,6 +89,7 @@ SIGNATURES = {
     "psgla_selftest_umma2": (_int, [_vp, _vp, _vp, _int, _vp]),
     "psgla_convg_layer": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "psgla_selftest_mma_rate": (_int, [_int, _int, _int, _int, _vp, _vp]),
+    "psgla_selftest_mma_rate2": (_int, [_int, _int, _int, _int, _vp, _vp]),
 }
 
 _lock = threading.Lock()

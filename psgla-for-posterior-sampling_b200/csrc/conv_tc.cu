@@ -128,7 +128,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, bool relu) {
 template <int NOUT, int NACC_>
 __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUtensorMap* tmap_out, uint8_t* stage,
                                                 const float* bias_s, uint64_t* tfull, uint64_t* tempty,
-                                                uint32_t tmem_base, int grp, int q4, int lane, uint32_t& T) {
+                                                uint32_t tmem_base, int grp, int q4, int lane, uint32_t& T,
+                                                uint32_t tempty_cluster = 0) {
+  // tempty_cluster != 0 (CTA-pair kernel): the accumulator-free barriers live in the leader CTA, at this cluster address.
   // T: the CTA's running output-row counter (accumulator stage and mbarrier phase); it carries over when one kernel
   // runs several layers back to back.  bias_s may point to shared or global memory.
   const uint32_t stage_row = smem_u32(stage) + lane * (NOUT * 2);
@@ -152,7 +154,10 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
       // the staging box of the previous row must have been read by its TMA store before it is overwritten
       if (lane == 0) {
         bulk_wait_group_read0();
-        mbar_arrive(&tempty[acc]);
+        if (tempty_cluster)
+          mbar_arrive_remote(tempty_cluster + acc * 8u);
+        else
+          mbar_arrive(&tempty[acc]);
       }
       __syncwarp();
       const bool has_res = p.res1 != nullptr && xw + lane < p.W;
@@ -518,9 +523,11 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 accumulate = 1;
               }
             }
+            // input row y - 1 is dead once its 12 MMAs (dy = 0) retire: free its TMEM slot now, two thirds of a row before
+            // the accumulator completes, so that the loaders run a full row ahead
+            if (dy == 0 && y - 1 >= c.ylo) umma_commit(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA]);
           }
           umma_commit(&tfull[acc]);
-          if (y - 1 >= c.ylo) umma_commit(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA]);
           if (y == ylast)
             for (int yy = y; yy <= c.yhi; ++yy) umma_commit(&aempty[(L0 + (uint32_t)(yy - c.ylo)) % TS_NA]);
         }
@@ -573,6 +580,218 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair TS kernel
+// The TS kernel above is bound by the shared-memory port, not the tensor pipe: per 128-pixel output row a CTA moves 72 KB
+// of B operand (36 MMAs x 2 KB of weights) next to the loaders', the TMA ring's and the epilogue's traffic.  cta_group::2
+// halves the dominant term: two CTAs on the SM pair of one TPC run ONE M = 256 MMA per (tap, K-step) -- 128 pixels (TMEM
+// lanes) in each CTA, the 64 output channels' weights split 32 / 32 between the two shared memories -- so every CTA reads
+// 1 KB instead of 2 KB of B per MMA and keeps only half of the layer's weights (36 KB).
+// The pair works on the two strips (2 sp, 2 sp + 1) of the same chain and row block, so every row count is identical in
+// both CTAs; the strip count is padded to even (a strip beyond the image loads zeros and stores nothing).
+// Roles per CTA as in the TS kernel; only the leader's warp 1 issues MMAs.  Barriers the leader's issuer waits on (afull,
+// tempty, wready) live in the leader and collect arrivals from both CTAs; barriers it signals (aempty, tfull, done) are
+// arrived in both CTAs by one multicast tcgen05.commit.
+constexpr int TS2_NSTAGE = 6;
+
+template <int NOUT>
+struct ConvTs2Cfg {
+  static constexpr int ROW_BYTES = 128;
+  static constexpr int BOX_BYTES = BOX_W * ROW_BYTES;
+  static constexpr int SLOT_BYTES = round_up_c(BOX_BYTES, 1024);
+  static constexpr int TAP_BYTES_FULL = NOUT * ROW_BYTES;       // one tap of the packed layer (all output channels)
+  static constexpr int TAP_BYTES = (NOUT / 2) * ROW_BYTES;      // this CTA's half
+  static constexpr int W_BYTES = 9 * TAP_BYTES;
+  static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
+  static constexpr int STAGE_BYTES = 32 * NOUT * 2;
+  static constexpr int OFF_STAGE = OFF_RING + TS2_NSTAGE * SLOT_BYTES;
+  static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + 256;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(TS_NACC * NOUT <= TS_A_COL0 && TS_A_COL0 + TS_NA * 96 <= 512, "TMEM plan does not fit 512 columns");
+  static_assert((2 * TS2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3) * 8 + 4 <= 256, "barrier block overflows");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
+};
+
+template <int NOUT>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  using Cfg = ConvTs2Cfg<NOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* ring = smem + Cfg::OFF_RING;
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // local: TMA landed a row in the staging ring
+  uint64_t* empty = full + TS2_NSTAGE;                                // local: loaders have copied it out
+  uint64_t* afull = empty + TS2_NSTAGE;                               // leader: both CTAs' copies of the row are in TMEM
+  uint64_t* aempty = afull + TS_NA;                                   // both (multicast): MMAs reading them completed
+  uint64_t* tfull = aempty + TS_NA;                                   // both (multicast): accumulator stage complete
+  uint64_t* tempty = tfull + TS_NACC;                                 // leader: both CTAs' epilogues drained the stage
+  uint64_t* wbar = tempty + TS_NACC;                                  // local: this CTA's half of the weights landed
+  uint64_t* wready = wbar + 1;                                        // leader: the peer's half landed
+  uint64_t* done = wready + 1;                                        // both (multicast): every MMA of the launch completed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  griddep_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TS2_NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 4);
+    }
+    for (int i = 0; i < TS_NA; ++i) {
+      mbar_init(&afull[i], 8);
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < TS_NACC; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    mbar_init(wbar, 1);
+    mbar_init(wready, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_ptr_s, 512);
+    tmem_relinquish2();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NOUT) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  tc_fence_before();
+  cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t afull_c = mapa_shared(smem_u32(afull), 0);
+  const uint32_t tempty_c = mapa_shared(smem_u32(tempty), 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      tma_prefetch_desc(&tmap);
+      mbar_expect_tx(wbar, Cfg::W_BYTES);
+      for (int t = 0; t < 9; ++t)
+        bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES,
+                  Cfg::TAP_BYTES, wbar);
+      if (rank != 0) {
+        mbar_wait(wbar, 0);
+        mbar_arrive_cluster(mapa_shared(smem_u32(wready), 0));
+      }
+      griddep_wait();
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
+          const uint32_t slot = L % TS2_NSTAGE;
+          mbar_wait(&empty[slot], ((L / TS2_NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
+          tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, y, c.b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer of the pair
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, NOUT);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+      const uint32_t w_lo = (smem_u32(smem_w) >> 4) | 0x10000u;
+      mbar_wait(wbar, 0);
+      mbar_wait_cluster(wready, 0);
+      tc_fence_after();
+      uint32_t L0 = 0, T = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        int waited = 0;
+        const int ylast = c.y0 + c.rcur - 1;
+        for (int y = c.y0; y <= ylast; ++y, ++T) {
+          const int need = min(y + 1, c.yhi) - c.ylo + 1;
+          while (waited < need) {
+            const uint32_t q = L0 + waited;
+            mbar_wait(&afull[q % TS_NA], (q / TS_NA) & 1);
+            ++waited;
+          }
+          const uint32_t acc = T % TS_NACC;
+          mbar_wait(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * NOUT;
+          if (elect_one()) {
+            uint32_t accumulate = 0;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int yy = y + dy - 1;
+              if (yy < 0 || yy >= p.H) continue;
+              const uint32_t q = L0 + (uint32_t)(yy - c.ylo);
+              const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
+                  umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              if (dy == 0 && y - 1 >= c.ylo) umma_commit2(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA], 3);
+            }
+            umma_commit2(&tfull[acc], 3);
+            if (y == ylast)
+              for (int yy = y; yy <= c.yhi; ++yy) umma_commit2(&aempty[(L0 + (uint32_t)(yy - c.ylo)) % TS_NA], 3);
+          }
+          __syncwarp();
+        }
+        L0 += (uint32_t)(c.yhi - c.ylo + 1);
+      }
+      if (elect_one()) umma_commit2(done, 3);
+      __syncwarp();
+    }
+    mbar_wait(done, 0);  // both CTAs: no MMA still reads this CTA's shared / tensor memory, no commit is still in flight
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- loaders: staging ring -> registers -> TMEM
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t ring_addr = smem_u32(ring);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TS_A_COL0;
+    uint32_t L = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
+        const uint32_t slot = L % TS2_NSTAGE, as = L % TS_NA;
+        mbar_wait(&full[slot], (L / TS2_NSTAGE) & 1);
+        mbar_wait(&aempty[as], ((L / TS_NA) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tile = ring_addr + slot * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          uint32_t v[32];
+          ld_swizzled_row128(tile, m + dx, v);
+          tmem_st_32x32b_x32(lane_taddr + as * 96u + dx * 32u, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&empty[slot]);
+          mbar_arrive_remote(afull_c + as * 8u);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
+    const int ew = warp - 6;
+    uint32_t T = 0;
+    epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
+                                   tmem_base, ew >> 2, warp & 3, lane, T, tempty_c);
+  }
+  tc_fence_before();
+  cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still signal or read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -936,6 +1155,77 @@ static int launch_conv_ts(const void* in, void* out_bf16, ConvParams p, cudaStre
 
 // A-operand source of the 64-input-channel layers: tensor memory (default) or shared memory (PSGLA_CONV_SS=1, kept for
 // A/B measurements and as the path of the 3-channel first layer).
+// Work items of the pair kernel: (chain, row block, strip) with the strip count padded to even and the strip index
+// fastest, so that items 2i and 2i + 1 -- the two CTAs of a cluster -- share chain and rows.
+static void plan_items_pair(ConvParams* p, int n_clusters) {
+  p->strips = ((p->W + TILE_M - 1) / TILE_M + 1) & ~1;
+  int best = 1;
+  long long best_cost = -1;
+  const int cands[] = {32, 16, 8, 4, 2, 1};
+  for (int R : cands) {
+    const long long pairs = (long long)p->B * (p->strips / 2) * ((p->H + R - 1) / R);
+    const long long cost = ((pairs + n_clusters - 1) / n_clusters) * (std::min(R, p->H) + 1);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = R;
+    }
+  }
+  const char* e = getenv("PSGLA_CONV_ROWS");
+  if (e && atoi(e) > 0) best = atoi(e);
+  p->R = best;
+  p->row_blocks = (p->H + best - 1) / best;
+  p->n_items = p->B * p->strips * p->row_blocks;
+}
+
+template <int NOUT>
+static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
+  using Cfg = ConvTs2Cfg<NOUT>;
+  CUtensorMap map, map_out;
+  int rc = get_act_tensor_map(&map, in, p.B, p.H, p.W, 64, BOX_W);
+  if (rc) return rc;
+  rc = get_act_tensor_map(&map_out, out_bf16, p.B, p.H, p.W, NOUT, 32);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  static int max_clusters = 0;  // CTA pairs the device holds at once (one CTA per SM)
+  if (!max_clusters) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts2_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
+    int n = 0;
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv3x3_ts2_kernel<NOUT>, &cfg));
+    max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
+    if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: conv3x3_ts2_kernel: %d co-resident CTA pairs (occupancy query %d)\n", max_clusters, n);
+  }
+  plan_items_pair(&p, max_clusters);
+  const int pairs = p.n_items / 2;
+  cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
+  if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: pair conv B=%d H=%d W=%d: R=%d items=%d grid=%u\n", p.B, p.H, p.W, p.R, p.n_items, cfg.gridDim.x);
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts2_kernel<NOUT>, map, map_out, p));
+  return PSGLA_OK;
+}
+
+// PSGLA_CONV_PAIR=0 falls back to the single-CTA TS kernel (A/B runs)
+static bool conv_use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSGLA_CONV_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static bool conv_use_ts() {
   static int v = -1;
   if (v < 0) {
@@ -945,7 +1235,8 @@ static bool conv_use_ts() {
   return v == 1;
 }
 static int launch_hidden64(const void* in, void* out, const ConvParams& p, cudaStream_t st) {
-  return conv_use_ts() ? launch_conv_ts<64, EPI_HIDDEN>(in, out, p, st) : launch_conv<64, 64, EPI_HIDDEN>(in, out, p, st);
+  if (!conv_use_ts()) return launch_conv<64, 64, EPI_HIDDEN>(in, out, p, st);
+  return conv_use_pair() ? launch_conv_ts2<64>(in, out, p, st) : launch_conv_ts<64, EPI_HIDDEN>(in, out, p, st);
 }
 static int launch_last(const void* in, const ConvParams& p, cudaStream_t st) {
   return conv_use_ts() ? launch_conv_ts<16, EPI_POST>(in, nullptr, p, st) : launch_conv<64, 16, EPI_POST>(in, nullptr, p, st);
@@ -1534,6 +1825,95 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
   }
 }
 }  // namespace psgla
+
+namespace psgla {
+// The same probe for a CTA pair: the leader issues `iters` x 4 K-steps of M256 x N x K16 MMAs (cta_group::2) on zeroed
+// operands, A from tensor memory (mode 0) or shared memory (mode 1), B split between the two shared memories.
+template <int mode>
+__global__ void __launch_bounds__(128, 1) mma_rate2_kernel(int n, int iters, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;                 // 128 rows x 128 B
+  uint8_t* sb = smem + 18 * 1024;     // up to 128 rows x 128 B (this CTA's half of N)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 52 * 1024);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 16);
+  for (int i = threadIdx.x; i < 52 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(tptr, 512);
+    tmem_relinquish2();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(256, n);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+      const uint32_t a_lo = (smem_u32(sa) >> 4) | 0x10000u;
+      const uint32_t b_lo = (smem_u32(sb) >> 4) | 0x10000u;
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (mode == 0)
+            umma_bf16_ts2(tbase, tbase + 256 + k * 8, ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+          else
+            umma_bf16_ss2(tbase, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc, 1);
+        }
+      }
+      umma_commit2(bar, 3);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    t1 = clock64();
+    if (rank == 0 && elect_one()) cycles[blockIdx.x >> 1] = t0 ? (t1 - t0) : 0;
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc2(tbase, 512);
+  }
+}
+}  // namespace psgla
+
+extern "C" int psgla_selftest_mma_rate2(int mode, int n, int iters, int n_pairs, long long* cycles_dev, void* stream) {
+  PSGLA_REQUIRE(cycles_dev && (mode == 0 || mode == 1) && n >= 32 && n <= 256 && n % 32 == 0 && iters > 0 && n_pairs > 0,
+                "psgla_selftest_mma_rate2: bad argument");
+  const int smem = 54 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (mode == 0)
+    PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_rate2_kernel<0>, n, iters, cycles_dev));
+  else
+    PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_rate2_kernel<1>, n, iters, cycles_dev));
+  return PSGLA_OK;
+}
 
 extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cycles_dev, void* stream) {
   PSGLA_REQUIRE(cycles_dev && mode >= 0 && mode <= 7 && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && grid > 0,

@@ -78,6 +78,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same without cluster-scope release semantics (ptxas turns those into MEMBAR.ALL.GPU + ERRBAR on every arrive and a
+// CCTL.IVALL on every acquiring wait): for barriers that only order tcgen05 traffic, which tcgen05.fence::before/after_
+// thread_sync already orders around the arrive / wait -- the form CUTLASS's ClusterBarrier::arrive(cta_id) uses.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait on a local mbarrier whose arrivals come from other CTAs of the cluster as well
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -368,6 +368,23 @@ def check_mma_pattern():
             print("mma_pattern %-32s N=%d: %.1f cycles/MMA" % (name, n, per), flush=True)
 
 
+def check_mma_rate2():
+    """cycles per M256 x N x K16 MMA of a CTA pair (cta_group::2)."""
+    import torch
+    import psgla_b200 as P
+    lib = P._lib.lib()
+    for pairs in (1, 74):
+        out = torch.zeros(pairs, dtype=torch.int64, device="cuda")
+        for mode, name in ((0, "TS"), (1, "SS")):
+            row = []
+            for n in (32, 64, 128, 256):
+                iters = 500
+                P._lib.check(lib.psgla_selftest_mma_rate2(mode, n, iters, pairs, out.data_ptr(), None), "mma_rate2")
+                torch.cuda.synchronize()
+                row.append("N=%d: %.1f" % (n, out.double().mean().item() / (iters * 4)))
+            print("mma_rate2 pairs=%d %s cycles/MMA  %s" % (pairs, name, "  ".join(row)), flush=True)
+
+
 def check_umma2():
     """cta_group::2 self-test: D[256 x 64] = A B^T by a CTA pair."""
     import torch
