@@ -299,6 +299,269 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair form
+// With both operands streaming, a single CTA moves (A + B) bytes into shared memory and (A + B) bytes out of it per
+// k-iteration: 64 KB per 256 MMA cycles at N = 128, 96 KB per 512 at N = 256 -- 250 / 187 B per clock against a 128 B/clk
+// port, which is where the measured 0.51 / 0.68 of the tensor peak come from.  cta_group::2 halves the B half of that: two
+// CTAs (one TPC) run one M = 256 MMA per K-step on two different pixel tiles, each streaming only N_TILE / 2 rows of
+// the weights.  Both producers signal the LEADER's "stage full" barrier (cp.async.bulk.tensor.cta_group::2), the leader
+// issues, and one multicast tcgen05.commit frees the stage in both CTAs.
+// Items: item = ((m_tile_pair * inner + sub) * 2 + rank), so the two CTAs of a cluster share (n tile, quadrant) and walk
+// the same (tap, k-block) sequence on M tiles 2 i and 2 i + 1; an odd M-tile count is padded with a tile at b = B, whose
+// loads are out of bounds (zero fill) and whose stores are masked.
+//
+// REUSE (3x3 layers whose rows are at least 128 pixels wide, tile = 128 pixels of one row): a stage holds ONE input-row box
+// of 130 pixels (halo left and right) and the weights of the three taps of that row (dx = 0, 1, 2, one 3-D box), and serves
+// 12 MMAs whose A descriptors start dx rows into the box -- a third of the activation traffic from L2 per MMA.  Without it
+// the 128-channel layers (4 MMAs of 64 cycles per 16 KB A box) sit at 0.65 of the tensor peak on L2 -> SM bandwidth.
+template <int N_TILE, bool REUSE>
+struct CgCfg2 {
+  static constexpr int THREADS = 64 + 32 * CG_EPI_WARPS;
+  static constexpr int A_BOX_BYTES = REUSE ? 130 * 128 : 128 * 128;
+  static constexpr int A_BYTES = REUSE ? 17 * 1024 : 128 * 128;
+  static constexpr int TAP_BYTES = (N_TILE / 2) * 128;          // this CTA's half of the N tile, one tap
+  static constexpr int B_BYTES = (REUSE ? 3 : 1) * TAP_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = (225280 / STAGE_BYTES) > 8 ? 8 : (225280 / STAGE_BYTES);
+  static constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = CG_NACC * N_TILE;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512 && TMEM_COLS >= 32, "TMEM columns");
+};
+
+__device__ __forceinline__ CgItem cg_decode2(const CgParams& p, int item) {
+  CgItem c;
+  const int inner = p.quads * p.n_tiles_n;
+  const int rank = item & 1;
+  const int t = item >> 1;
+  const int sub = t % inner;
+  int mt = 2 * (t / inner) + rank;
+  c.q = sub / p.n_tiles_n;
+  c.n0 = sub % p.n_tiles_n;
+  const int tx = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int ty = mt % p.tiles_y;
+  c.b = mt / p.tiles_y;  // == p.B for the padding tile
+  c.x0 = tx * p.PX;
+  c.y0 = ty * p.ROWS;
+  return c;
+}
+
+template <int N_TILE, bool REUSE>
+__global__ void __launch_bounds__((CgCfg2<N_TILE, REUSE>::THREADS), 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const CgParams p) {
+  using Cfg = CgCfg2<N_TILE, REUSE>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // leader: both CTAs' boxes of the stage landed
+  uint64_t* empty = full + NSTAGE;                                    // both (multicast): the stage's MMAs completed
+  uint64_t* tfull = empty + NSTAGE;                                   // both (multicast): accumulator complete
+  uint64_t* tempty = tfull + CG_NACC;                                 // leader: both epilogues drained the stage
+  uint64_t* done = tempty + CG_NACC;                                  // both (multicast): all MMAs of the launch completed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  griddep_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < CG_NACC; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_ptr_s, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int kiters = (REUSE ? 3 : p.taps) * p.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_w);
+      const uint32_t full_c = mapa_shared(smem_u32(full), 0);
+      const uint32_t stage_tx = 2u * (uint32_t)((REUSE ? Cfg::A_BOX_BYTES : p.PX * p.ROWS * 128) + Cfg::B_BYTES);
+      const int nrow0 = (int)rank * (N_TILE / 2);
+      griddep_wait();
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const CgItem c = cg_decode2(p, item);
+        if (REUSE) {
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int kb = 0; kb < p.kblocks; ++kb, ++L) {
+              const uint32_t slot = L % NSTAGE;
+              mbar_wait(&empty[slot], ((L / NSTAGE) & 1) ^ 1);
+              uint8_t* sa = smem + slot * Cfg::STAGE_BYTES;
+              const uint32_t bar = full_c + slot * 8u;
+              if (rank == 0) mbar_expect_tx(&full[slot], stage_tx);
+              tma_load_4d_2sm(sa, &map_a, bar, kb * 64, c.x0 - 1, c.y0 + dy - 1, c.b);                 // 130 pixels of one row
+              tma_load_3d_2sm(sa + Cfg::A_BYTES, &map_w, bar, kb * 64, c.n0 * N_TILE + nrow0, dy * 3);  // taps 3 dy .. 3 dy + 2
+            }
+          }
+          continue;
+        }
+        for (int t = 0; t < p.taps; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++L) {
+            const uint32_t slot = L % NSTAGE;
+            mbar_wait(&empty[slot], ((L / NSTAGE) & 1) ^ 1);
+            uint8_t* sa = smem + slot * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            const uint32_t bar = full_c + slot * 8u;
+            if (rank == 0) mbar_expect_tx(&full[slot], stage_tx);
+            if (p.mode == CG_CONV3) {
+              tma_load_4d_2sm(sa, &map_a, bar, kb * 64, c.x0 + (t % 3) - 1, c.y0 + (t / 3) - 1, c.b);
+              tma_load_3d_2sm(sb, &map_w, bar, kb * 64, c.n0 * N_TILE + nrow0, t);
+            } else if (p.mode == CG_DOWN2) {
+              tma_load_5d_2sm(sa, &map_a, bar, kb * 64, t & 1, c.x0, t >> 1, c.b * (p.Hin / 2) + c.y0);
+              tma_load_3d_2sm(sb, &map_w, bar, kb * 64, c.n0 * N_TILE + nrow0, t);
+            } else {
+              tma_load_4d_2sm(sa, &map_a, bar, kb * 64, c.x0, c.y0, c.b);
+              tma_load_3d_2sm(sb, &map_w, bar, kb * 64, c.n0 * N_TILE + nrow0, c.q);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer of the pair
+      constexpr uint32_t idesc = make_idesc_bf16(256, N_TILE);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+      const uint32_t smem_lo = (smem_u32(smem) >> 4) | 0x10000u;
+      uint32_t L = 0, T = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++T) {
+        const uint32_t acc = T % CG_NACC;
+        mbar_wait(&tempty[acc], ((T / CG_NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int it = 0; it < kiters; ++it, ++L) {
+          const uint32_t slot = L % NSTAGE;
+          mbar_wait(&full[slot], (L / NSTAGE) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = smem_lo + slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+            const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
+            if (REUSE) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // A: the row box read from pixel dx on (whole 128-byte rows keep the swizzle phase)
+                  umma_bf16_ss2(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + (uint32_t)(dx * 8 + k * 2)),
+                                ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)(dx * (Cfg::TAP_BYTES >> 4) + k * 2)), idesc,
+                                (it | dx | k) != 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss2(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + k * 2), ((uint64_t)DESC_HI << 32) | (b_lo + k * 2), idesc,
+                              (it | k) != 0);
+            }
+            umma_commit2(&empty[slot], 3);
+            if (it == kiters - 1) umma_commit2(&tfull[acc], 3);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit2(done, 3);
+      __syncwarp();
+    }
+    mbar_wait(done, 0);
+  } else {
+    // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps (each CTA its own M tile)
+    // A thread owns one pixel: N_TILE consecutive channels of the output (and of the residual inputs).  The first residual
+    // tensor is fetched into registers BEFORE the accumulator is awaited (the item's MMAs take thousands of cycles, the
+    // loads a few hundred), 128 channels at a time; for N_TILE = 256 the registers of a finished 32-channel chunk are
+    // refilled with the chunk 128 channels further on while the remaining chunks are processed.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const int r = m / p.PX, px = m % p.PX;
+    const bool relu = p.relu != 0;
+    const uint32_t tempty_c = mapa_shared(smem_u32(tempty), 0);
+    constexpr int NB = N_TILE / 128;  // batches of 128 channels
+    griddep_wait();
+    uint32_t T = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++T) {
+      if ((int)(T & 1) != grp) continue;
+      const CgItem c = cg_decode2(p, item);
+      const uint32_t acc = T % CG_NACC;
+      const int yg = c.y0 + r, xg = c.x0 + px;
+      const bool valid = (m < p.PX * p.ROWS) && yg < p.Hg && xg < p.Wg && c.b < p.B;
+      int yo = yg, xo = xg;
+      if (p.mode == CG_UP2) {
+        yo = 2 * yg + (c.q >> 1);
+        xo = 2 * xg + (c.q & 1);
+      }
+      const size_t off = (((size_t)c.b * p.Hout + yo) * p.Wout + xo) * p.Cout + (size_t)c.n0 * N_TILE;
+      const bool has_res = valid && p.res1 != nullptr;
+      uint4 rr[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rr[j] = *reinterpret_cast<const uint4*>(p.res1 + off + j * 8);
+      }
+      mbar_wait(&tfull[acc], (T / CG_NACC) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * N_TILE;
+#pragma unroll
+      for (int hb = 0; hb < NB; ++hb) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int ch = hb * 4 + c4;  // 32-channel chunk
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == N_TILE / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_c + acc * 8u);
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
+              const size_t o = off + ch * 32 + j * 8;
+              if (has_res) {
+                cg_add_bf16x8(f, rr[c4 * 4 + j]);
+                if (hb + 1 < NB) rr[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res1 + o + 128);
+              }
+              if (p.res2) cg_add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + o));
+              uint4 w;
+              w.x = cg_pack(f[0], f[1], relu);
+              w.y = cg_pack(f[2], f[3], relu);
+              w.z = cg_pack(f[4], f[5], relu);
+              w.w = cg_pack(f[6], f[7], relu);
+              *reinterpret_cast<uint4*>(p.out + o) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int cg_encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                      const cuuint32_t* box) {
@@ -357,6 +620,38 @@ static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParam
   return PSGLA_OK;
 }
 
+template <int N_TILE, bool REUSE>
+static int cg_launch2(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p, cudaStream_t st) {
+  using Cfg = CgCfg2<N_TILE, REUSE>;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
+    int n = 0;
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE>, &cfg));
+    max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
+  }
+  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int pairs = ((m_tiles + 1) / 2) * p.quads * p.n_tiles_n;
+  p.n_items = 2 * pairs;
+  cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<N_TILE, REUSE>, ma, mw, p));
+  return PSGLA_OK;
+}
+
 // One layer.  in: bf16 NHWC [B][Hin][Win][Cin]; w: bf16 [taps][Cout][Cin]; out: bf16 NHWC (CONV3: same extent, DOWN2:
 // half, UP2: double); res1 / res2: optional tensors of the output's shape added before the optional ReLU.
 int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const void* w, const void* in, const void* res1,
@@ -391,7 +686,21 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
     cg_mode = e ? atoi(e) : 0;
   }
   const bool ts = cg_mode == 1;
+  // PSGLA_CG_PAIR=0: single-CTA kernels everywhere (A/B runs); default: the CTA-pair kernel for N tiles of 128 and 256
+  static int cg_pair = -1;
+  if (cg_pair < 0) {
+    const char* e = getenv("PSGLA_CG_PAIR");
+    cg_pair = (e && e[0] == '0') ? 0 : 1;
+  }
   const int n_tile = (!ts && Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  const bool pair = cg_pair && !ts && n_tile >= 128;
+  // one 130-pixel row box for the three horizontal taps (CgCfg2<., true>): 3x3 layers with rows of >= 128 pixels
+  static int cg_reuse = -1;
+  if (cg_reuse < 0) {
+    const char* e = getenv("PSGLA_CG_REUSE");
+    cg_reuse = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool reuse = pair && cg_reuse && mode == CG_CONV3 && p.PX == 128 && p.ROWS == 1;
   p.n_tiles_n = Cout / n_tile;
   p.n_items = B * p.tiles_y * p.tiles_x * p.quads * p.n_tiles_n;
   p.relu = relu;
@@ -409,18 +718,22 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
   } else {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)p.PX, (cuuint32_t)p.ROWS, 1};
-    rc = cg_cached_map(&ma, CgMapKey{in, 4, B, Hin, Win, Cin, p.PX * 1000 + p.ROWS}, 4, dims, strides, box);
+    const int box_px = reuse ? 130 : p.PX;
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_px, (cuuint32_t)p.ROWS, 1};
+    rc = cg_cached_map(&ma, CgMapKey{in, 4, B, Hin, Win, Cin, box_px * 1000 + p.ROWS}, 4, dims, strides, box);
   }
   if (rc) return rc;
   {
     const int taps_total = mode == CG_UP2 ? 4 : p.taps;
     const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps_total};
     const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    const cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
-    rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, Cout, taps_total, n_tile, 0}, 3, dims, strides, box);
+    const int box_n = pair ? n_tile / 2 : n_tile;  // a CTA of a pair streams half of the N tile
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_n, reuse ? 3u : 1u};
+    rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, Cout, taps_total, box_n, reuse ? 3 : 1}, 3, dims, strides, box);
   }
   if (rc) return rc;
+  if (reuse) return n_tile == 256 ? cg_launch2<256, true>(ma, mw, p, st) : cg_launch2<128, true>(ma, mw, p, st);
+  if (pair) return n_tile == 256 ? cg_launch2<256, false>(ma, mw, p, st) : cg_launch2<128, false>(ma, mw, p, st);
   if (n_tile == 256) return cg_launch<256, false>(ma, mw, p, st);
   if (n_tile == 128) return ts ? cg_launch<128, true>(ma, mw, p, st) : cg_launch<128, false>(ma, mw, p, st);
   return ts ? cg_launch<64, true>(ma, mw, p, st) : cg_launch<64, false>(ma, mw, p, st);

@@ -137,12 +137,23 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
   const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
   const bool relu = p.relu != 0;
   if (lane == 0) tma_prefetch_desc(tmap_out);
+  // the residual tensors come from earlier kernels and are now read ahead of the accumulator (i.e. before anything in this
+  // warp depends on the producer's own griddepcontrol.wait)
+  if (p.res1 != nullptr) griddep_wait();
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     const ItemCoord c = decode_item(p, item);
     const int xw = c.x0 + q4 * 32;  // first pixel of this warp's 32-pixel box
     for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
       if ((int)(T & 1) != grp) continue;
       const uint32_t acc = T % NACC_;
+      // residual inputs (DRUNet) are fetched while the row's MMAs are still in flight
+      const bool has_res = p.res1 != nullptr && xw + lane < p.W;
+      const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
+      uint4 rr[NOUT / 8];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < NOUT / 8; ++j) rr[j] = *reinterpret_cast<const uint4*>(p.res1 + roff + 8 * j);
+      }
       mbar_wait(&tfull[acc], (T / NACC_) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
@@ -160,8 +171,6 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
           mbar_arrive(&tempty[acc]);
       }
       __syncwarp();
-      const bool has_res = p.res1 != nullptr && xw + lane < p.W;
-      const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
 #pragma unroll
       for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
         const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
@@ -170,7 +179,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
                       __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
                       __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
         if (has_res) {
-          add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res1 + roff + 8 * j));
+          add_bf16x8(f, rr[j]);
           if (p.res2) add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j));
         }
         uint4 o;

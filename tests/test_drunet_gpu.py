@@ -46,6 +46,9 @@ def _tol(ref):
     (2, 8, 8, 512, 512, 1, True),      # deepest scale, 8 k-blocks
     (1, 7, 130, 64, 192, 0, False),    # N tile 64 x 3, odd extents
     (1, 1, 1, 128, 128, 0, False),
+    (1, 5, 128, 128, 128, 1, True),    # CTA-pair kernel, one 130-pixel row box for the three horizontal taps; odd M-tile count
+    (3, 3, 300, 128, 128, 2, True),    # same with three strips per row (ragged last strip), 27 M tiles
+    (1, 4, 256, 256, 256, 0, False),   # row-box form at N tile 256
 ])
 def test_conv3x3_general(B, H, W, Cin, Cout, res, relu):
     g = torch.Generator(device="cuda").manual_seed(0)
