@@ -378,14 +378,16 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "gpu_launches": 21 * K,
         "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
                 "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
-        "roofline": {"kernel": "conv3x3_kernel<64,64,EPI_HIDDEN> (18 of the 21 launches per iteration)", "bound": "tensor",
+        "roofline": {"kernel": "conv3x3_ts2_kernel<64> (CTA-pair tcgen05 implicit GEMM; 18 of the 21 launches per iteration)", "bound": "tensor",
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms,
-                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01e_conv3x3_ts_full.txt): 272.9 MB read +
-                     # 220.4 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2
-                     "traffic": 493.3e6 if (B == 32 and H == 256) else None,
-                     "traffic_source": "profiles/r01e_conv3x3_ts_full.txt"},
+                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01f_conv3x3_ts2_full.txt): 273.7 MB read +
+                     # 218.4 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2.
+                     # Same capture: tensor pipe active 75.2 % of the active cycles (single-CTA TS kernel: 62.4 %).
+                     "traffic": 492.2e6 if (B == 32 and H == 256) else None,
+                     "traffic_source": "profiles/r01f_conv3x3_ts2_full.txt",
+                     "ncu_tensor_pipe_active_pct": 75.2},
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -508,10 +510,16 @@ def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
         "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 69 * K,
         "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
                 "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
-        "roofline": {"kernel": "whole iteration: 1 pre + 68 conv launches (conv_gemm_kernel<128|256>, conv3x3_ts_kernel<64>)",
+        "roofline": {"kernel": "whole iteration: 1 pre + 68 conv launches (CTA-pair kernels conv_gemm2_kernel<128|256> and "
+                               "conv3x3_ts2_kernel<64>; conv_gemm_kernel<64> for the 64-channel up-conv)",
                      "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": tflops / peaks["bf16_tflops"],
-                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "traffic": None},
+                     "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "traffic": None,
+                     # one ncu --set full capture of this workload's 256-channel 3x3 layer (64 chains, 80 x 120 pixels):
+                     # 466 us = 1 555 TFLOP/s useful, tensor pipe active 97.9 % of the active cycles at 1.50 GHz
+                     "dominant_kernel_ncu": {"kernel": "conv_gemm2_kernel<256,false>", "tensor_pipe_active_pct": 97.9,
+                                             "launch_us": 466.5, "dram_bytes": 588.5e6,
+                                             "source": "profiles/r01f_conv_gemm2_full.txt"}},
         "state_finite": finite, "per_step_ms": [round(v, 3) for v in per_step],
     }
 
