@@ -330,26 +330,54 @@ blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const
     gys[i] = wrap(x0 - L + lane + 32 * i, W);
   }
   float res[3][4], xc[3][4];
-
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
+  // Global -> register staging of one channel's tile: every load of the channel is issued before the first dependent
+  // store (an in-order warp otherwise pays one DRAM round trip per staged row), and channel c + 1 is fetched while
+  // channel c runs its four passes.
+  constexpr int XR = (SW + 7) / 8, YR = (W1 + 7) / 8;        // staged rows per warp
+  constexpr int XI = (SW + 31) / 32, YI = (W1 + 31) / 32;    // staged columns per lane
+  float xv[XR][XI], yv[FULL ? YR : 1][FULL ? YI : 1];
+  auto fetch = [&](int c) {
     const float* xp = x + ((long long)b * 3 + c) * plane;
-    __syncthreads();  // previous channel's readers of s0 / s1 are done
-    for (int r = warp; r < SW; r += 8) {
-      const float* row = xp + (long long)wrap(y0 - HALO + r, H) * W;
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (lane + 32 * i < SW) s0[r * SW + lane + 32 * i] = row[gxs[i]];
+    for (int k = 0; k < XR; ++k) {
+      const int r = warp + 8 * k;
+      const float* row = xp + (long long)wrap(y0 - HALO + min(r, SW - 1), H) * W;
+#pragma unroll
+      for (int i = 0; i < XI; ++i) xv[k][i] = (r < SW && lane + 32 * i < SW) ? row[gxs[i]] : 0.f;
     }
     if (FULL) {
       const float* yp = y + ((long long)(y_B > 1 ? b : 0) * 3 + c) * plane;
-      for (int r = warp; r < W1; r += 8) {
-        const float* row = yp + (long long)wrap(y0 - L + r, H) * W;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (lane + 32 * i < W1) sy[r * W1 + lane + 32 * i] = row[gys[i]];
+      for (int k = 0; k < YR; ++k) {
+        const int r = warp + 8 * k;
+        const float* row = yp + (long long)wrap(y0 - L + min(r, W1 - 1), H) * W;
+#pragma unroll
+        for (int i = 0; i < YI; ++i) yv[k][i] = (r < W1 && lane + 32 * i < W1) ? row[gys[i]] : 0.f;
       }
     }
+  };
+  fetch(0);
+
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    __syncthreads();  // previous channel's readers of s0 / s1 are done
+#pragma unroll
+    for (int k = 0; k < XR; ++k) {
+      const int r = warp + 8 * k;
+#pragma unroll
+      for (int i = 0; i < XI; ++i)
+        if (r < SW && lane + 32 * i < SW) s0[r * SW + lane + 32 * i] = xv[k][i];
+    }
+    if (FULL) {
+#pragma unroll
+      for (int k = 0; k < YR; ++k) {
+        const int r = warp + 8 * k;
+#pragma unroll
+        for (int i = 0; i < YI; ++i)
+          if (r < W1 && lane + 32 * i < W1) sy[r * W1 + lane + 32 * i] = yv[k][i];
+      }
+    }
+    if (c < 2) fetch(c + 1);
     __syncthreads();
     {
       const float4 v = *reinterpret_cast<const float4*>(s0 + (HALO + prow) * SW + HALO + pcol);  // x at the owned pixels
