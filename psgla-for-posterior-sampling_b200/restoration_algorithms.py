@@ -6,7 +6,8 @@ tensors.  Per iteration the host issues two C-ABI calls: the fused Langevin "pre
 whose last layer's epilogue applies the denoiser term, thins samples and updates the running moments.
 Extra keyword-only arguments:
   noise          tensor (n_iter, *init.shape) of N(0,1) draws to replay (e.g. the reference's torch.randn stream)
-  rng            "philox" (default: in-kernel Philox4x32-10, keyed by seed / chain id / iteration), "torch"
+  rng            default: "torch_cuda" for a single chain (so that ``seed=k`` alone reproduces the reference's CUDA run), "philox"
+                 when ``n_chains`` is given.  "philox": in-kernel Philox4x32-10, keyed by seed / chain id / iteration; "torch"
                  (draw ``torch.randn(im_shape, generator=Generator(device).manual_seed(seed))`` per iteration exactly
                  like the reference and replay it) or "torch_cuda" (the same stream as "torch" on a CUDA device, generated
                  bit for bit inside the fused kernel from the seed alone: no randn launch, no noise tensor)
@@ -80,6 +81,8 @@ class _Run:
         self.noise = noise
         self.gen = None
         self.torch_threads = self.torch_step = 0
+        if rng is None:
+            rng = "torch_cuda" if n_chains is None else "philox"
         if noise is None and rng == "torch":
             self.gen = torch.Generator(device=self.device)
             self.gen.manual_seed(self.seed)
@@ -178,7 +181,7 @@ def _save_online(path, name, i, run, extra):
 
 
 def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
-              n_inter_mmse=1000, seed=None, *, noise=None, rng="philox", n_chains=None, chain_id0=0):
+              n_inter_mmse=1000, seed=None, *, noise=None, rng=None, n_chains=None, chain_id0=0):
     """The stepping object behind ``psgla``: ``run.step(i)`` issues iteration i (one "pre" launch + the DnCNN layer
     chain); ``run.Xlist`` / ``run.Xlist_mmse`` / ``run.Xlist_mmse2`` are the reference's three lists."""
     run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
@@ -200,7 +203,7 @@ def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4
 
 def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
           n_inter_mmse=1000, seed=None, device=None, path=None, save_images_online=False, name=None, *, noise=None,
-          rng="philox", n_chains=None, chain_id0=0):
+          rng=None, n_chains=None, chain_id0=0):
     """PSGLA (restoration_algorithms.py:163-285):  Y = X + (delta/lambd) data_grad(X) + sqrt(2) sig Z;
     X = (1 - alpha) Y + alpha D(Y).  Returns (Xlist, Xlist_mmse, Xlist_mmse2)."""
     run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, n_inter, n_inter_mmse, seed,
@@ -215,7 +218,7 @@ def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5,
 
 
 def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
-               c_min=-1, c_max=2, *, noise=None, rng="philox", n_chains=None, chain_id0=0):
+               c_min=-1, c_max=2, *, noise=None, rng=None, n_chains=None, chain_id0=0):
     """The stepping object behind ``pnpula`` (see ``psgla_run``)."""
     if not isinstance(prior_grad, PriorGrad):
         raise TypeError("prior_grad must be a PriorGrad(denoiser, alpha, s1, s2) structured callable")
@@ -237,7 +240,7 @@ def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1
 
 
 def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
-           device=None, c_min=-1, c_max=2, path=None, save_images_online=False, name=None, *, noise=None, rng="philox",
+           device=None, c_min=-1, c_max=2, path=None, save_images_online=False, name=None, *, noise=None, rng=None,
            n_chains=None, chain_id0=0):
     """PnP-ULA (restoration_algorithms.py:38-160):
     X+ = X + delta (prior_grad(X) - (X - proj_[c_min,c_max] X)/lambd + data_grad(X)) + sqrt(2 delta) Z."""
@@ -261,7 +264,7 @@ def pnp(init, data_grad, Pb, denoiser, alpha, lambd, sig_float=0.0055, delta=1e-
     data_grad(X); X = (1 - alpha) Y + alpha D(Y; sig_den), sig_den = 40/255 for the first n_iter // 10 iterations of an
     inpainting problem, else sig_float (only DRUNet reads it).  Returns (all iterates, [last iterate], [])."""
     run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, 1, max(int(n_iter), 1), seed=0,
-                    n_chains=n_chains)
+                    rng="philox", n_chains=n_chains)
     run.pre_params.noise_scale = 0.0
     print("delta = {}, sigma = {}".format(delta, sig_float))
     sig32 = float(np.float32(sig_float))

@@ -86,3 +86,33 @@ def test_torch_stream_argument_errors():
     assert lib.psgla_img_noise_torch_cuda(16, 0, 2, 256, out.data_ptr(), None) == -1  # offset not a multiple of 4
     assert lib.psgla_img_noise_torch_cuda(16, 0, 0, 100, out.data_ptr(), None) == -1  # threads not a multiple of 256
     assert b"psgla_img_noise_torch_cuda" in lib.psgla_last_error()
+
+
+@pytest.mark.parametrize("problem", ["inpainting", "deblurring"])
+def test_seed_only_drop_in_against_the_reference_algorithm_on_cuda(problem):
+    """The drop-in property the torch stream buys: the reference algorithm (oracle restatement, bit-identical to the
+    unmodified reference on the CPU, run here on cuda with ITS OWN torch.Generator(seed)) and psgla(..., seed=seed,
+    rng="torch_cuda") consume the same noise without any tensor crossing between them; what remains is the bf16 denoiser
+    against the fp32 one.  Tolerance 2e-2 abs on iterates in [0, 1] over 6 iterations (observed ~1e-4), bookkeeping exact."""
+    sd = io_.make_dncnn_weights(seed=0, n_power_iter=5, spatial=16)
+    den = P.DnCNN(pretrained=sd)
+    net = io_.DnCNN().cuda()
+    net.load_state_dict(sd)
+    torch.manual_seed(2)
+    im = torch.rand(1, 3, 64, 64, device="cuda")
+    if problem == "inpainting":
+        dg, init, _, _ = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    else:
+        dg, init, _ = P.make_deblurring(im, l=4, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("psgla")
+    kw = dict(alpha=torch.tensor(1.0, device="cuda"), lambd=torch.tensor(prm["lambd"], device="cuda"), sig_float=prm["s"],
+              delta=prm["delta"], n_iter=6, n_inter=2, n_inter_mmse=2, seed=5)
+    Xr, Mr, M2r = io_.psgla(init, dg, net.eval(), device="cuda", **kw)
+    Xg, Mg, M2g = P.psgla(init, dg, den, rng="torch_cuda", **kw)
+    torch.cuda.synchronize()
+    assert len(Xr) == len(Xg) == 3 and len(Mr) == len(Mg) == 2 and len(M2r) == len(M2g) == 2
+    for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
+        assert (a - b).abs().max().item() < 2e-2
+    # and the noise really is the same: with a different seed the iterates differ at the noise scale
+    Xo, _, _ = P.psgla(init, dg, den, rng="torch_cuda", **dict(kw, seed=6))
+    assert (Xo[0] - Xg[0]).abs().max().item() > 1e-2
