@@ -375,7 +375,7 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
                                "(seeded random-init, Lipschitz 0.9), %d chains/GPU of %dx%dx3, in-kernel Philox" % (B, H, Wd),
                    "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
         "dtype": "bf16 activations / fp32 accumulate, fp32 state",
-        "gpu_launches": 21 * K,
+        "gpu_launches": 20 * K,  # 20 conv launches; the Langevin pre / post steps live in the last layer's epilogue
         "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
                 "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
         "roofline": {"kernel": "conv3x3_ts2_kernel<64> (CTA-pair tcgen05 implicit GEMM; 18 of the 21 launches per iteration)", "bound": "tensor",

@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PSGLA_ABI_VERSION 3
+#define PSGLA_ABI_VERSION 4
 
 enum {
   PSGLA_OK = 0,
@@ -41,7 +41,7 @@ enum {
 const char* psgla_last_error(void);
 int psgla_abi_version(void);
 /* sizeof() of the structs below as the library was compiled (0: psgla_gmm2d_problem, 1: psgla_img_shape, 2: psgla_pre_params,
- * 3: psgla_post_params; -1 otherwise) -- lets a binding verify its struct layout. */
+ * 3: psgla_post_params, 4: psgla_next_pre; -1 otherwise) -- lets a binding verify its struct layout. */
 int psgla_struct_size(int which);
 /* Philox4x32-10 (Salmon et al., SC'11) block function as the kernels use it: counter[4], key[2] -> out[4].  Host code,
  * no GPU needed; the tests pin it to the Random123 known-answer vectors. */
@@ -216,6 +216,24 @@ int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgla_img_shape
                               const psgla_post_params* post, float* x_out_dev, float* sample_dev, float* mean_dev,
                               float* mean2_dev, void* stream);
 
+/* The same with the NEXT iteration's inpainting "pre" fused into the epilogue: the thread that has just produced X+ for a
+ * pixel also evaluates psgla_img_pre_inpaint's arithmetic on it (same noise element, bit-identical results) and writes the
+ * next base and denoiser input, so that a sampler iteration is the conv launches alone.  next == NULL: plain post.
+ * base_dev / den_in_dev of `next` may be this call's base_dev / den_in_dev (in place: every element is read before it is
+ * rewritten by the same thread, and den_in was consumed by the first layer). */
+typedef struct psgla_next_pre {
+  const psgla_pre_params* pre; /* parameters of iteration i + 1 (its `iteration`, torch_offset, ...) */
+  const float* mask_dev;       /* [1 or B][C][H][W] */
+  const float* y_dev;
+  int32_t mask_B, y_B;
+  float* base_dev;             /* out: [B][C][H][W] fp32 */
+  void* den_in_dev;            /* out: bf16 NHWC [B][H][W][16] */
+} psgla_next_pre;
+int psgla_dncnn_residual_post_next(int depth, const void* packed_dev, psgla_img_shape shape, const void* den_in_dev,
+                                   void* workspace_dev, size_t workspace_bytes, const float* base_dev,
+                                   const psgla_post_params* post, float* x_out_dev, float* sample_dev, float* mean_dev,
+                                   float* mean2_dev, const psgla_next_pre* next, void* stream);
+
 /* Single conv3x3 layers, exposed for parity tests against torch.nn.functional.conv2d.
  *   cin_pad: 16 (first layer, channels 3..15 zero) or 64.   in_dev: bf16 NHWC [B][H][W][cin_pad].
  *   out_dev: bf16 NHWC [B][H][W][64], ReLU applied if relu != 0.   layer: index into the packed weights. */
@@ -256,6 +274,10 @@ size_t psgla_drunet_workspace_bytes(psgla_img_shape shape);
 int psgla_drunet_denoise_post(const void* packed_dev, psgla_img_shape shape, const void* den_in_dev, void* workspace_dev,
                               size_t workspace_bytes, const float* base_dev, const psgla_post_params* post,
                               float* x_out_dev, float* sample_dev, float* mean_dev, float* mean2_dev, void* stream);
+int psgla_drunet_denoise_post_next(const void* packed_dev, psgla_img_shape shape, const void* den_in_dev, void* workspace_dev,
+                                   size_t workspace_bytes, const float* base_dev, const psgla_post_params* post,
+                                   float* x_out_dev, float* sample_dev, float* mean_dev, float* mean2_dev,
+                                   const psgla_next_pre* next, void* stream);
 
 /* One general convolution layer of the DRUNet denoiser (deepinv.models.DRUNet, sampling_images.py:136) as implicit GEMM:
  *   mode 0: 3x3 stride 1 zero-pad 1 (Cin -> Cout); 1: 2x2 stride 2 (downsampling); 2: 2x2 stride 2 transposed (upsampling).

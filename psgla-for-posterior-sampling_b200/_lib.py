@@ -48,6 +48,12 @@ class PostParams(C.Structure):
     _fields_ = [("gain", C.c_float), ("base_scale", C.c_float), ("w_old", C.c_float), ("w_new", C.c_float)]
 
 
+class NextPre(C.Structure):
+    """psgla_next_pre"""
+    _fields_ = [("pre", C.POINTER(PreParams)), ("mask_dev", C.c_void_p), ("y_dev", C.c_void_p), ("mask_B", C.c_int32),
+                ("y_B", C.c_int32), ("base_dev", C.c_void_p), ("den_in_dev", C.c_void_p)]
+
+
 _vp, _i64, _u64, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/psgla_b200.h declares
@@ -76,6 +82,8 @@ SIGNATURES = {
     "psgla_dncnn_workspace_bytes": (_sz, [ImgShape]),
     "psgla_dncnn_residual_post": (_int, [_int, _vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp,
                                          _vp, _vp]),
+    "psgla_dncnn_residual_post_next": (_int, [_int, _vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp,
+                                              _vp, C.POINTER(NextPre), _vp]),
     "psgla_conv3x3_layer": (_int, [_vp, _int, _int, ImgShape, _vp, _vp, _int, _vp]),
     "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, C.c_float, _vp, _vp]),
     "psgla_img_metrics_workspace_bytes": (_sz, [_int]),
@@ -85,6 +93,8 @@ SIGNATURES = {
     "psgla_drunet_pack_weights": (_int, [C.POINTER(C.POINTER(C.c_float)), _vp, _vp]),
     "psgla_drunet_workspace_bytes": (_sz, [ImgShape]),
     "psgla_drunet_denoise_post": (_int, [_vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp, _vp, _vp]),
+    "psgla_drunet_denoise_post_next": (_int, [_vp, ImgShape, _vp, _vp, _sz, _vp, C.POINTER(PostParams), _vp, _vp, _vp, _vp,
+                                              C.POINTER(NextPre), _vp]),
     "psgla_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "psgla_selftest_umma2": (_int, [_vp, _vp, _vp, _int, _vp]),
     "psgla_convg_layer": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
@@ -111,7 +121,7 @@ def lib() -> C.CDLL:
                     fn = getattr(handle, name)  # AttributeError if the header and the library disagree
                     fn.restype = res
                     fn.argtypes = args
-                for which, struct in enumerate((GmmProblem, ImgShape, PreParams, PostParams)):
+                for which, struct in enumerate((GmmProblem, ImgShape, PreParams, PostParams, NextPre)):
                     if handle.psgla_struct_size(which) != C.sizeof(struct):
                         raise RuntimeError("ctypes layout of %s (%d bytes) disagrees with libpsgla_b200.so (%d bytes): "
                                            "rebuild the library" % (struct.__name__, C.sizeof(struct), handle.psgla_struct_size(which)))

@@ -3,7 +3,12 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "../../include/psgla_b200.h"
+
 namespace psgla {
+
+// validates a psgla_next_pre (inpainting "pre" of the next iteration, fused into the last layer's epilogue)
+int check_next_pre(const psgla_next_pre* next, const psgla_img_shape& shape);
 
 // conv_tc.cu -- layers whose weights stay resident in shared memory
 void pack_conv3x3_swizzled(const float* w, int nout_real, int cin_real, int nout_pad, int cin_pad, uint8_t* dst);
@@ -13,7 +18,7 @@ int conv_first16(const void* in16, void* out, const uint8_t* w, const float* bia
                  cudaStream_t st);
 int conv_last_post(const void* in, const uint8_t* w, const float* bias, int B, int H, int W, const float* base,
                    float base_scale, float gain, float w_old, float w_new, float* x_out, float* sample, float* mean,
-                   float* mean2, cudaStream_t st);
+                   float* mean2, const psgla_next_pre* next, cudaStream_t st);
 
 // conv_gemm.cu -- layers with streamed weights (mode: 0 conv3x3, 1 2x2 stride-2 down, 2 2x2 transposed up)
 int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const void* w, const void* in, const void* res1,

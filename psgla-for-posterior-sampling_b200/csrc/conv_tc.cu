@@ -26,6 +26,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_api.cuh"
+#include "langevin.cuh"
 #include "sm100.cuh"
 
 namespace psgla {
@@ -90,7 +92,18 @@ struct ConvParams {
   float* mean;
   float* mean2;
   float gain, base_scale, w_old, w_new;
+  // EPI_POST, optional: the "pre" step of the NEXT iteration applied to the iterate this epilogue produces (inpainting):
+  // nx_base = langevin_base(X+), nx_den_in = bf16 NHWC16 of it (PSGLA) or of X+ (PnP-ULA); nx_base may alias base.
+  int nx_enable;
+  PreArgs nx;
+  const float* nx_mask;
+  const float* nx_y;
+  int nx_mask_B, nx_y_B;
+  float* nx_base;
+  __nv_bfloat16* nx_den_in;
 };
+
+static int set_next_pre(ConvParams* p, const psgla_next_pre* next);  // host: fills the nx_* fields (defined with the API)
 
 struct ItemCoord {
   int b, y0, rcur, x0, ylo, yhi;
@@ -213,9 +226,11 @@ __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* 
     const bool valid = x < p.W;
     for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
       if ((int)(T & 1) != grp) continue;
-      // fetch this pixel's base / running moments while the MMAs of the row are still in flight
+      // fetch this pixel's base / running moments (and the next iteration's mask / observation) while the MMAs of the row
+      // are still in flight
       const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
       float bse[3] = {0.f, 0.f, 0.f}, m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
+      float nmask[3] = {0.f, 0.f, 0.f}, nobs[3] = {0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -223,6 +238,16 @@ __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* 
           if (p.mean) {
             m1[ch] = p.mean[idx0 + ch * plane];
             m2[ch] = p.mean2[idx0 + ch * plane];
+          }
+        }
+        if (p.nx_enable) {
+          const size_t e0 = (size_t)y * p.W + x;
+          const size_t mi = ((size_t)(p.nx_mask_B > 1 ? c.b : 0) * 3) * plane + e0;
+          const size_t yi = ((size_t)(p.nx_y_B > 1 ? c.b : 0) * 3) * plane + e0;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            nmask[ch] = p.nx_mask[mi + ch * plane];
+            nobs[ch] = p.nx_y[yi + ch * plane];
           }
         }
       }
@@ -237,11 +262,13 @@ __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (valid) {
+        float xnew[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const size_t idx = idx0 + ch * plane;
           const float r = __uint_as_float(v[ch]) + bias_s[ch];
           const float xn = p.base ? fmaf(p.gain, r, p.base_scale * bse[ch]) : r;
+          xnew[ch] = xn;
           p.x_out[idx] = xn;
           if (p.sample) p.sample[idx] = xn;
           if (p.mean) {
@@ -249,6 +276,20 @@ __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* 
             p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, m1[ch]), __fmul_rn(p.w_new, xn));
             p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
           }
+        }
+        if (p.nx_enable) {
+          // the next iteration's Langevin "pre" on the fresh iterate: same arithmetic and the same noise element as
+          // pre_inpaint_kernel (img_elementwise.cu), so fused and unfused runs agree bit for bit
+          float din[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const uint32_t e = (uint32_t)((size_t)ch * plane + (size_t)y * p.W + x);
+            const float z = draw_at(p.nx, c.b, e);
+            const float bv = langevin_base(p.nx, xnew[ch], nmask[ch] * (xnew[ch] - nobs[ch]), z);
+            p.nx_base[idx0 + ch * plane] = bv;
+            din[ch] = (p.nx.alg == PSGLA_ALG_PNPULA) ? xnew[ch] : bv;
+          }
+          store_nhwc16(p.nx_den_in + (((size_t)c.b * plane) + (size_t)y * p.W + x) * 16, din[0], din[1], din[2], p.nx.den_in_c3);
         }
       }
     }
@@ -1399,8 +1440,21 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
                                          const void* den_in_dev, void* workspace_dev, size_t workspace_bytes,
                                          const float* base_dev, const psgla_post_params* post, float* x_out_dev,
                                          float* sample_dev, float* mean_dev, float* mean2_dev, void* stream) {
+  return psgla_dncnn_residual_post_next(depth, packed_dev, shape, den_in_dev, workspace_dev, workspace_bytes, base_dev, post,
+                                        x_out_dev, sample_dev, mean_dev, mean2_dev, nullptr, stream);
+}
+
+extern "C" int psgla_dncnn_residual_post_next(int depth, const void* packed_dev, psgla_img_shape shape,
+                                              const void* den_in_dev, void* workspace_dev, size_t workspace_bytes,
+                                              const float* base_dev, const psgla_post_params* post, float* x_out_dev,
+                                              float* sample_dev, float* mean_dev, float* mean2_dev,
+                                              const psgla_next_pre* next, void* stream) {
   PSGLA_REQUIRE(packed_dev && den_in_dev && workspace_dev && post && x_out_dev && depth >= 2,
                 "psgla_dncnn_residual_post: bad argument");
+  {
+    const int rcn = check_next_pre(next, shape);
+    if (rcn) return rcn;
+  }
   PSGLA_REQUIRE((mean_dev == nullptr) == (mean2_dev == nullptr), "mean and mean2 must be given together");
   int rc = check_shape(shape);
   if (rc) return rc;
@@ -1446,6 +1500,8 @@ extern "C" int psgla_dncnn_residual_post(int depth, const void* packed_dev, psgl
   p.base_scale = 1.0f;  // DnCNN is a residual denoiser: X+ = base + gain * R
   p.w_old = post->w_old;
   p.w_new = post->w_new;
+  rc = set_next_pre(&p, next);
+  if (rc) return rc;
   return launch_last(cur, p, st);
 }
 
@@ -1492,9 +1548,35 @@ int conv_first16(const void* in16, void* out, const uint8_t* w, const float* bia
   return launch_conv<16, 64, EPI_HIDDEN>(in16, out, p, st);
 }
 
+int check_next_pre(const psgla_next_pre* next, const psgla_img_shape& s) {
+  if (!next) return PSGLA_OK;
+  PSGLA_REQUIRE(next->pre && next->mask_dev && next->y_dev && next->base_dev && next->den_in_dev,
+                "psgla_next_pre: null pointer");
+  PSGLA_REQUIRE((next->mask_B == 1 || next->mask_B == s.B) && (next->y_B == 1 || next->y_B == s.B),
+                "psgla_next_pre: mask_B / y_B must be 1 or B");
+  PreArgs a;
+  return fill_pre(next->pre, &a);
+}
+
+static int set_next_pre(ConvParams* p, const psgla_next_pre* next) {
+  p->nx_enable = 0;
+  if (!next) return PSGLA_OK;
+  int rc = fill_pre(next->pre, &p->nx);
+  if (rc) return rc;
+  p->nx.chw = 3LL * p->H * p->W;
+  p->nx_enable = 1;
+  p->nx_mask = next->mask_dev;
+  p->nx_y = next->y_dev;
+  p->nx_mask_B = next->mask_B;
+  p->nx_y_B = next->y_B;
+  p->nx_base = next->base_dev;
+  p->nx_den_in = (__nv_bfloat16*)next->den_in_dev;
+  return PSGLA_OK;
+}
+
 int conv_last_post(const void* in, const uint8_t* w, const float* bias, int B, int H, int W, const float* base,
                    float base_scale, float gain, float w_old, float w_new, float* x_out, float* sample, float* mean,
-                   float* mean2, cudaStream_t st) {
+                   float* mean2, const psgla_next_pre* next, cudaStream_t st) {
   ConvParams p{};
   p.B = B, p.H = H, p.W = W;
   p.weights = w;
@@ -1508,6 +1590,8 @@ int conv_last_post(const void* in, const uint8_t* w, const float* bias, int B, i
   p.sample = sample;
   p.mean = mean;
   p.mean2 = mean2;
+  int rc = set_next_pre(&p, next);
+  if (rc) return rc;
   return launch_last(in, p, st);
 }
 

@@ -39,6 +39,7 @@ extern "C" int psgla_struct_size(int which) {
     case 1: return (int)sizeof(psgla_img_shape);
     case 2: return (int)sizeof(psgla_pre_params);
     case 3: return (int)sizeof(psgla_post_params);
+    case 4: return (int)sizeof(psgla_next_pre);
     default: return -1;
   }
 }

@@ -140,7 +140,19 @@ extern "C" int psgla_drunet_denoise_post(const void* packed_dev, psgla_img_shape
                                          void* workspace_dev, size_t workspace_bytes, const float* base_dev,
                                          const psgla_post_params* post, float* x_out_dev, float* sample_dev,
                                          float* mean_dev, float* mean2_dev, void* stream) {
+  return psgla_drunet_denoise_post_next(packed_dev, shape, den_in_dev, workspace_dev, workspace_bytes, base_dev, post, x_out_dev,
+                                        sample_dev, mean_dev, mean2_dev, nullptr, stream);
+}
+
+extern "C" int psgla_drunet_denoise_post_next(const void* packed_dev, psgla_img_shape shape, const void* den_in_dev,
+                                              void* workspace_dev, size_t workspace_bytes, const float* base_dev,
+                                              const psgla_post_params* post, float* x_out_dev, float* sample_dev,
+                                              float* mean_dev, float* mean2_dev, const psgla_next_pre* next, void* stream) {
   PSGLA_REQUIRE(packed_dev && den_in_dev && workspace_dev && post && x_out_dev, "psgla_drunet_denoise_post: null pointer");
+  {
+    const int rcn = check_next_pre(next, shape);
+    if (rcn) return rcn;
+  }
   PSGLA_REQUIRE((mean_dev == nullptr) == (mean2_dev == nullptr), "mean and mean2 must be given together");
   PSGLA_REQUIRE(shape.B > 0 && shape.C == 3 && shape.H > 0 && shape.W > 0, "image shape must be [B>0][3][H>0][W>0]");
   PSGLA_REQUIRE(shape.H % 8 == 0 && shape.W % 8 == 0, "DRUNet needs H and W to be multiples of 8 (got %d x %d): crop or pad "
@@ -215,5 +227,5 @@ extern "C" int psgla_drunet_denoise_post(const void* packed_dev, psgla_img_shape
   }
   // tail + fused Langevin post:  X+ = base_scale * base + gain * D
   return conv_last_post(cur, wptr(li), bias_of(li, 16, 64), B, H, W, base_dev, post->base_scale, post->gain, post->w_old,
-                        post->w_new, x_out_dev, sample_dev, mean_dev, mean2_dev, st);
+                        post->w_new, x_out_dev, sample_dev, mean_dev, mean2_dev, next, st);
 }

@@ -113,14 +113,16 @@ class DnCNN:
             self._den_in = torch.empty(n_in, dtype=torch.bfloat16, device=self.device)
         return self._ws, self._den_in
 
-    def residual_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None):
+    def residual_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None, next_pre=None):
+        """``next_pre``: a ``_lib.NextPre`` -- the next iteration's inpainting "pre" fused into the last layer's epilogue."""
         ws, _ = self.buffers(shape)
         with torch.cuda.device(self.device):
-            rc = _lib.lib().psgla_dncnn_residual_post(self.depth, _lib.ptr(self.packed), shape, _lib.ptr(den_in),
-                                                      _lib.ptr(ws), ws.numel(), _lib.ptr(base), C.byref(post),
-                                                      _lib.ptr(x_out), _lib.ptr(sample), _lib.ptr(mean), _lib.ptr(mean2),
-                                                      _lib.stream_ptr(self.device))
-        _lib.check(rc, "psgla_dncnn_residual_post")
+            rc = _lib.lib().psgla_dncnn_residual_post_next(self.depth, _lib.ptr(self.packed), shape, _lib.ptr(den_in),
+                                                           _lib.ptr(ws), ws.numel(), _lib.ptr(base), C.byref(post),
+                                                           _lib.ptr(x_out), _lib.ptr(sample), _lib.ptr(mean), _lib.ptr(mean2),
+                                                           C.byref(next_pre) if next_pre is not None else None,
+                                                           _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_dncnn_residual_post_next")
 
     def forward(self, x, sigma=None):
         """D(x) = x + R(x), fp32 [B,3,H,W] in and out (``sigma`` ignored, as in deepinv's DnCNN)."""
@@ -236,13 +238,15 @@ class DRUNet:
             self._den_in = torch.empty(n_in, dtype=torch.bfloat16, device=self.device)
         return self._ws, self._den_in
 
-    def apply_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None):
+    def apply_post(self, shape, den_in, base, post, x_out, sample=None, mean=None, mean2=None, next_pre=None):
         ws, _ = self.buffers(shape)
         with torch.cuda.device(self.device):
-            rc = _lib.lib().psgla_drunet_denoise_post(_lib.ptr(self.packed), shape, _lib.ptr(den_in), _lib.ptr(ws), ws.numel(),
-                                                      _lib.ptr(base), C.byref(post), _lib.ptr(x_out), _lib.ptr(sample),
-                                                      _lib.ptr(mean), _lib.ptr(mean2), _lib.stream_ptr(self.device))
-        _lib.check(rc, "psgla_drunet_denoise_post")
+            rc = _lib.lib().psgla_drunet_denoise_post_next(_lib.ptr(self.packed), shape, _lib.ptr(den_in), _lib.ptr(ws),
+                                                           ws.numel(), _lib.ptr(base), C.byref(post), _lib.ptr(x_out),
+                                                           _lib.ptr(sample), _lib.ptr(mean), _lib.ptr(mean2),
+                                                           C.byref(next_pre) if next_pre is not None else None,
+                                                           _lib.stream_ptr(self.device))
+        _lib.check(rc, "psgla_drunet_denoise_post_next")
 
     def forward(self, x, sigma):
         if not x.is_cuda:

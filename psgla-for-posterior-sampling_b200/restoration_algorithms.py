@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -110,11 +111,20 @@ class _Run:
 
     def configure(self, pre, gain, base_scale=1.0):
         self.pre_params, self.gain, self.base_scale = pre, float(gain), float(base_scale)
+        self.fuse_next_pre, self._pre_done_for = os.environ.get("PSGLA_FUSE_PRE", "1") != "0", None
+        self._next_params = _lib.PreParams()
 
     def step(self, i):
-        """Iteration i of the sampler: fused Langevin "pre" kernel, then DnCNN + fused "post" epilogue."""
-        self.pre(i, self.pre_params)
-        self.post(i, self.gain)
+        """Iteration i of the sampler.  Inpainting (``fuse_next_pre``): the conv launches alone -- the last layer's epilogue
+        applies the denoiser term, thins, updates the moments AND evaluates iteration i + 1's Langevin "pre" on the fresh
+        iterate; only the first iteration of a run of consecutive steps launches the stand-alone "pre" kernel.  Deblurring
+        (a stencil: neighbours needed): "pre" kernel, then the conv launches."""
+        fuse = self.fuse_next_pre and self.mask is not None and self.noise is None and self.gen is None
+        if not fuse or self._pre_done_for != i:
+            self.pre(i, self.pre_params)
+        nxt = i + 1 if (fuse and i + 1 < self.n_iter) else None
+        self.post(i, self.gain, next_iteration=nxt)
+        self._pre_done_for = nxt
 
     def _out(self, t):
         return t[0] if self.squeeze else t
@@ -126,13 +136,16 @@ class _Run:
             return torch.randn(self.X.shape, generator=self.gen, dtype=torch.float32, device=self.device)
         return None
 
-    def pre(self, i, pre: "_lib.PreParams"):
-        z = self.z_for(i)
+    def _stamp(self, pre, i):
         pre.seed, pre.chain_id0, pre.iteration = self.seed, self.chain_id0, i
         if self.torch_threads:
             pre.noise_mode, pre.torch_threads, pre.torch_offset = _lib.NOISE_TORCH_CUDA, self.torch_threads, i * self.torch_step
         else:
             pre.noise_mode = _lib.NOISE_PHILOX
+
+    def pre(self, i, pre: "_lib.PreParams"):
+        z = self.z_for(i)
+        self._stamp(pre, i)
         lib = _lib.lib()
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
@@ -147,11 +160,19 @@ class _Run:
                                               _lib.ptr(self.den_in), st)
                 _lib.check(rc, "psgla_img_pre_deblur")
 
-    def post(self, i, gain):
+    def post(self, i, gain, next_iteration=None):
         k = self.iter_mmse
         post = _lib.PostParams(float(gain), self.base_scale, float(np.float32(k / (k + 1))), float(np.float32(1 / (k + 1))))
         sample = self.samples[i // self.n_inter] if i % self.n_inter == 0 else None
-        self.den.apply_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2)
+        nxt = None
+        if next_iteration is not None:
+            if self.noise is not None or self.gen is not None:
+                raise RuntimeError("the fused next-iteration pre generates its noise in the kernel (rng 'philox' / 'torch_cuda')")
+            C.memmove(C.byref(self._next_params), C.byref(self.pre_params), C.sizeof(_lib.PreParams))
+            self._stamp(self._next_params, next_iteration)
+            nxt = _lib.NextPre(C.pointer(self._next_params), _lib.ptr(self.mask), _lib.ptr(self.y), int(self.mask.shape[0]),
+                               int(self.y.shape[0]), _lib.ptr(self.base), _lib.ptr(self.den_in))
+        self.den.apply_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2, next_pre=nxt)
         if sample is not None:
             self.Xlist.append(self._out(sample))
         # window bookkeeping exactly as restoration_algorithms.py:128-144 / :255-271
@@ -266,6 +287,7 @@ def pnp(init, data_grad, Pb, denoiser, alpha, lambd, sig_float=0.0055, delta=1e-
     run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, 1, max(int(n_iter), 1), seed=0,
                     rng="philox", n_chains=n_chains)
     run.pre_params.noise_scale = 0.0
+    run.fuse_next_pre = False  # the noise-level map of iteration i + 1 is only known at iteration i + 1 (annealing schedule)
     print("delta = {}, sigma = {}".format(delta, sig_float))
     sig32 = float(np.float32(sig_float))
     for i in range(run.n_iter):
@@ -290,6 +312,7 @@ def red(init, data_grad, Pb, denoiser, lambd, sig_float=0.0055, delta=1e-5, n_it
     pre.noise_scale, pre.proj_gain, pre.c_min, pre.c_max = 0.0, 0.0, 0.0, 0.0
     pre.x_gain = 0.0 if denoiser.is_residual else -g
     run.configure(pre, g)
+    run.fuse_next_pre = False
     print("delta = {}, sigma = {}".format(delta, sig_float))
     sig32 = float(np.float32(sig_float))
     for i in range(run.n_iter):

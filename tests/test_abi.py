@@ -32,7 +32,7 @@ def test_library_exports_every_symbol(built):
     handle = ctypes.CDLL(built._lib.LIB_PATH)
     for fn in _header_functions():
         assert hasattr(handle, fn), fn
-    assert handle.psgla_abi_version() == 3
+    assert handle.psgla_abi_version() == 4
 
 
 def test_struct_sizes_match_header(built):
@@ -41,7 +41,8 @@ def test_struct_sizes_match_header(built):
     assert ctypes.sizeof(L.ImgShape) == 16
     assert ctypes.sizeof(L.PreParams) == 72
     assert ctypes.sizeof(L.PostParams) == 16
-    for which, struct in enumerate((L.GmmProblem, L.ImgShape, L.PreParams, L.PostParams)):  # as compiled into the .so
+    assert ctypes.sizeof(L.NextPre) == 48
+    for which, struct in enumerate((L.GmmProblem, L.ImgShape, L.PreParams, L.PostParams, L.NextPre)):  # as compiled into the .so
         assert L.lib().psgla_struct_size(which) == ctypes.sizeof(struct)
 
 
