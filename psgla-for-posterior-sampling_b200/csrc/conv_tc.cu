@@ -36,7 +36,7 @@ using namespace sm100;
 
 constexpr int TILE_M = 128;
 constexpr int BOX_W = TILE_M + 2;
-constexpr int NSTAGE = 6;     // input-row ring slots
+constexpr int NSTAGE_64 = 6;   // input-row ring slots, 64-channel rows (17 KB each); 16-channel rows: ConvCfg::NSTAGE
 constexpr int NACC = 4;       // TMEM accumulator stages; stage s is drained by epilogue group s & 1
 constexpr int EPI_WARPS = 8;  // two groups of four warps (one warp per TMEM lane quarter)
 constexpr int CONV_THREADS = 64 + 32 * EPI_WARPS;
@@ -66,11 +66,20 @@ struct ConvCfg {
   static constexpr int TAP_BYTES = NOUT * ROW_BYTES;
   static constexpr int W_BYTES = 9 * TAP_BYTES;
   static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
-  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? 32 * NOUT * 2 : 0;  // one 32-pixel output box per epilogue warp
+  // 32-pixel output boxes per epilogue warp: two (the warp fills one while the TMA store of the previous row still reads
+  // the other) where shared memory allows, i.e. not next to 72 KB of weights and a 64-channel ring
+  // Ring depth.  A slot stays occupied for three output rows, so NSTAGE - 3 rows are in flight ahead of the MMAs; the
+  // 16-channel first layer consumes a row in ~430 cycles against ~2 us of TMA latency from HBM and needs a deep ring
+  // (6 slots: 1 560 cycles per row measured), its rows are only 5 KB.
+  static constexpr int NSTAGE = (CIN == 16) ? 20 : NSTAGE_64;
+  static constexpr int STAGE_BUFS = (CIN == 16) ? 2 : 1;
+  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? STAGE_BUFS * 32 * NOUT * 2 : 0;
   static constexpr int OFF_STAGE = OFF_RING + NSTAGE * SLOT_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 256;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + slack to align the dynamic base to 1024
+  static constexpr int BAR_BYTES = 512;
+  static_assert((2 * NSTAGE + 2 * NACC + 1) * 8 + 4 <= BAR_BYTES, "barrier block overflows");
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;  // + slack to align the dynamic base to 1024
   static constexpr int TMEM_COLS = (NACC * NOUT) < 32 ? 32 : NACC * NOUT;
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
@@ -142,11 +151,13 @@ template <int NOUT, int NACC_>
 __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUtensorMap* tmap_out, uint8_t* stage,
                                                 const float* bias_s, uint64_t* tfull, uint64_t* tempty,
                                                 uint32_t tmem_base, int grp, int q4, int lane, uint32_t& T,
-                                                uint32_t tempty_cluster = 0) {
+                                                uint32_t tempty_cluster = 0, int stage_bufs = 1) {
   // tempty_cluster != 0 (CTA-pair kernel): the accumulator-free barriers live in the leader CTA, at this cluster address.
   // T: the CTA's running output-row counter (accumulator stage and mbarrier phase); it carries over when one kernel
   // runs several layers back to back.  bias_s may point to shared or global memory.
-  const uint32_t stage_row = smem_u32(stage) + lane * (NOUT * 2);
+  // stage_bufs == 2: the warp alternates between two staging boxes, so a row is staged while the previous row's TMA
+  // store is still reading its box (the store's read latency otherwise serialises with the warp's work on every row)
+  uint32_t nrow = 0;
   const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
   const bool relu = p.relu != 0;
   if (lane == 0) tma_prefetch_desc(tmap_out);
@@ -176,8 +187,14 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
       tmem_ld_wait();
       tc_fence_before();
       // the staging box of the previous row must have been read by its TMA store before it is overwritten
+      uint8_t* stage_cur = stage + (stage_bufs == 2 ? (nrow & 1u) * (32 * NOUT * 2) : 0);
+      const uint32_t stage_row = smem_u32(stage_cur) + lane * (NOUT * 2);
+      ++nrow;
       if (lane == 0) {
-        bulk_wait_group_read0();
+        if (stage_bufs == 2)
+          bulk_wait_group_read1();
+        else
+          bulk_wait_group_read0();
         if (tempty_cluster)
           mbar_arrive_remote(tempty_cluster + acc * 8u);
         else
@@ -204,95 +221,166 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && xw < p.W) {
-        tma_store_4d(tmap_out, stage, 0, xw, y, c.b);
-        bulk_commit_group();
+      if (lane == 0) {
+        if (xw < p.W) tma_store_4d(tmap_out, stage_cur, 0, xw, y, c.b);
+        bulk_commit_group();  // also when nothing was stored: wait_group.read 1 counts one group per row
       }
     }
   }
   if (lane == 0) bulk_wait_group0();
 }
 
-// Last layer: the fused Langevin "post" step, fp32 NCHW (restoration_algorithms.py:238-262 / :115-135).
+// Last layer: the fused Langevin "post" step, fp32 NCHW (restoration_algorithms.py:238-262 / :115-135), optionally followed
+// by the next iteration's "pre" on the fresh iterate.
+// The layer is HBM-bound (128 B of activations in, ~70-140 B of fp32 state in and out per pixel) and its MMAs take only a few
+// hundred cycles per row, so nothing hides a DRAM round trip behind them: the epilogue therefore walks ITS rows with a
+// one-row-ahead register prefetch of everything it reads from global memory, and draws the row's noise before it waits
+// for the accumulator.
+struct PostRowIter {
+  int item, y, yend;
+  uint32_t T;
+  ItemCoord c;
+  bool done;
+};
+struct PostRowData {
+  float bse[3], m1[3], m2[3], nmask[3], nobs[3];
+};
+
 template <int NOUT, int NACC_>
 __device__ __forceinline__ void epilogue_post(const ConvParams& p, const float* bias_s, uint64_t* tfull, uint64_t* tempty,
                                               uint32_t tmem_base, int grp, int q4, int lane) {
   griddep_wait();  // base / running moments were written by earlier kernels
   const size_t plane = (size_t)p.H * p.W;
-  uint32_t T = 0;
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const ItemCoord c = decode_item(p, item);
-    const int x = c.x0 + q4 * 32 + lane;
-    const bool valid = x < p.W;
-    for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
-      if ((int)(T & 1) != grp) continue;
-      // fetch this pixel's base / running moments (and the next iteration's mask / observation) while the MMAs of the row
-      // are still in flight
-      const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
-      float bse[3] = {0.f, 0.f, 0.f}, m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f};
-      float nmask[3] = {0.f, 0.f, 0.f}, nobs[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          if (p.base) bse[ch] = p.base[idx0 + ch * plane];
-          if (p.mean) {
-            m1[ch] = p.mean[idx0 + ch * plane];
-            m2[ch] = p.mean2[idx0 + ch * plane];
-          }
-        }
-        if (p.nx_enable) {
-          const size_t e0 = (size_t)y * p.W + x;
-          const size_t mi = ((size_t)(p.nx_mask_B > 1 ? c.b : 0) * 3) * plane + e0;
-          const size_t yi = ((size_t)(p.nx_y_B > 1 ? c.b : 0) * 3) * plane + e0;
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            nmask[ch] = p.nx_mask[mi + ch * plane];
-            nobs[ch] = p.nx_y[yi + ch * plane];
-          }
-        }
-      }
-      const uint32_t acc = T % NACC_;
-      mbar_wait(&tfull[acc], (T / NACC_) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(taddr, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (valid) {
-        float xnew[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const size_t idx = idx0 + ch * plane;
-          const float r = __uint_as_float(v[ch]) + bias_s[ch];
-          const float xn = p.base ? fmaf(p.gain, r, p.base_scale * bse[ch]) : r;
-          xnew[ch] = xn;
-          p.x_out[idx] = xn;
-          if (p.sample) p.sample[idx] = xn;
-          if (p.mean) {
-            // three rounded fp32 operations each, as the reference's eager ops (restoration_algorithms.py:257-258)
-            p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, m1[ch]), __fmul_rn(p.w_new, xn));
-            p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
-          }
-        }
-        if (p.nx_enable) {
-          // the next iteration's Langevin "pre" on the fresh iterate: same arithmetic and the same noise element as
-          // pre_inpaint_kernel (img_elementwise.cu), so fused and unfused runs agree bit for bit
-          float din[3];
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const uint32_t e = (uint32_t)((size_t)ch * plane + (size_t)y * p.W + x);
-            const float z = draw_at(p.nx, c.b, e);
-            const float bv = langevin_base(p.nx, xnew[ch], nmask[ch] * (xnew[ch] - nobs[ch]), z);
-            p.nx_base[idx0 + ch * plane] = bv;
-            din[ch] = (p.nx.alg == PSGLA_ALG_PNPULA) ? xnew[ch] : bv;
-          }
-          store_nhwc16(p.nx_den_in + (((size_t)c.b * plane) + (size_t)y * p.W + x) * 16, din[0], din[1], din[2], p.nx.den_in_c3);
-        }
+  auto step = [&](PostRowIter& r) {
+    ++r.y;
+    ++r.T;
+    if (r.y >= r.yend) {
+      r.item += gridDim.x;
+      if (r.item >= p.n_items) {
+        r.done = true;
+      } else {
+        r.c = decode_item(p, r.item);
+        r.y = r.c.y0;
+        r.yend = r.c.y0 + r.c.rcur;
       }
     }
+  };
+  auto settle = [&](PostRowIter& r) {  // forward to the next row this epilogue group drains
+    while (!r.done && (int)(r.T & 1) != grp) step(r);
+  };
+  auto fetch = [&](const PostRowIter& r, PostRowData& d) {
+    const int x = r.c.x0 + q4 * 32 + lane;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) d.bse[ch] = d.m1[ch] = d.m2[ch] = d.nmask[ch] = d.nobs[ch] = 0.f;
+    if (r.done || x >= p.W) return;
+    const size_t e0 = (size_t)r.y * p.W + x;
+    const size_t idx0 = ((size_t)r.c.b * 3) * plane + e0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (p.base) d.bse[ch] = p.base[idx0 + ch * plane];
+      if (p.mean) {
+        d.m1[ch] = p.mean[idx0 + ch * plane];
+        d.m2[ch] = p.mean2[idx0 + ch * plane];
+      }
+    }
+    if (p.nx_enable) {
+      const size_t mi = ((size_t)(p.nx_mask_B > 1 ? r.c.b : 0) * 3) * plane + e0;
+      const size_t yi = ((size_t)(p.nx_y_B > 1 ? r.c.b : 0) * 3) * plane + e0;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        d.nmask[ch] = p.nx_mask[mi + ch * plane];
+        d.nobs[ch] = p.nx_y[yi + ch * plane];
+      }
+    }
+  };
+
+  PostRowIter it;
+  it.item = blockIdx.x;
+  it.T = 0;
+  it.done = it.item >= p.n_items;
+  if (!it.done) {
+    it.c = decode_item(p, it.item);
+    it.y = it.c.y0;
+    it.yend = it.c.y0 + it.c.rcur;
+  }
+  settle(it);
+  PostRowData cur;
+  fetch(it, cur);
+  while (!it.done) {
+    PostRowIter nxt = it;
+    step(nxt);
+    settle(nxt);
+    PostRowData nd;
+    fetch(nxt, nd);  // in flight while this row is processed
+    const ItemCoord& c = it.c;
+    const int y = it.y;
+    const uint32_t T = it.T;
+    const int x = c.x0 + q4 * 32 + lane;
+    const bool valid = x < p.W;
+    const size_t idx0 = ((size_t)c.b * 3) * plane + (size_t)y * p.W + x;
+    float z[3] = {0.f, 0.f, 0.f};
+    if (p.nx_enable) {
+      if (p.nx.noise_mode == PSGLA_NOISE_PHILOX && (p.W & 3) == 0) {
+        // Library stream: one Philox call serves four consecutive elements, and lanes 4k .. 4k+3 hold four consecutive
+        // pixels (x0, the warp offset and W are multiples of 4).  Lane 4k + ch draws channel ch's quad, the four lanes
+        // exchange components by shuffle: one Philox call per lane instead of three.
+        const int sub = lane & 3;
+        float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sub < 3 && x - sub < p.W)
+          draw_quad(p.nx, c.b, (uint32_t)((size_t)sub * plane + (size_t)y * p.W + (size_t)(x - sub)), z4);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int src = (lane & ~3) + ch;
+          const float t0 = __shfl_sync(0xffffffffu, z4[0], src), t1 = __shfl_sync(0xffffffffu, z4[1], src);
+          const float t2 = __shfl_sync(0xffffffffu, z4[2], src), t3 = __shfl_sync(0xffffffffu, z4[3], src);
+          z[ch] = sub == 0 ? t0 : (sub == 1 ? t1 : (sub == 2 ? t2 : t3));
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) z[ch] = draw_at(p.nx, c.b, (uint32_t)((size_t)ch * plane + (size_t)y * p.W + x));
+      }
+    }
+    const uint32_t acc = T % NACC_;
+    mbar_wait(&tfull[acc], (T / NACC_) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(taddr, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[acc]);
+    if (valid) {
+      float xnew[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const size_t idx = idx0 + ch * plane;
+        const float r = __uint_as_float(v[ch]) + bias_s[ch];
+        const float xn = p.base ? fmaf(p.gain, r, p.base_scale * cur.bse[ch]) : r;
+        xnew[ch] = xn;
+        p.x_out[idx] = xn;
+        if (p.sample) p.sample[idx] = xn;
+        if (p.mean) {
+          // three rounded fp32 operations each, as the reference's eager ops (restoration_algorithms.py:257-258)
+          p.mean[idx] = __fadd_rn(__fmul_rn(p.w_old, cur.m1[ch]), __fmul_rn(p.w_new, xn));
+          p.mean2[idx] = __fadd_rn(__fmul_rn(p.w_old, cur.m2[ch]), __fmul_rn(p.w_new, __fmul_rn(xn, xn)));
+        }
+      }
+      if (p.nx_enable) {
+        // the next iteration's Langevin "pre" on the fresh iterate: same arithmetic and the same noise element as
+        // pre_inpaint_kernel (img_elementwise.cu), so fused and unfused runs agree bit for bit
+        float din[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float bv = langevin_base(p.nx, xnew[ch], cur.nmask[ch] * (xnew[ch] - cur.nobs[ch]), z[ch]);
+          p.nx_base[idx0 + ch * plane] = bv;
+          din[ch] = (p.nx.alg == PSGLA_ALG_PNPULA) ? xnew[ch] : bv;
+        }
+        store_nhwc16(p.nx_den_in + (((size_t)c.b * plane) + (size_t)y * p.W + x) * 16, din[0], din[1], din[2], p.nx.den_in_c3);
+      }
+    }
+    it = nxt;
+    cur = nd;
   }
 }
 
@@ -301,6 +389,7 @@ template <int CIN, int NOUT, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   using Cfg = ConvCfg<CIN, NOUT, EPI>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
@@ -424,7 +513,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint32_t T = 0;
     if (EPI == EPI_HIDDEN)
       epilogue_hidden<NOUT, NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                  tmem_base, ew >> 2, warp & 3, lane, T);
+                                  tmem_base, ew >> 2, warp & 3, lane, T, 0, Cfg::STAGE_BUFS);
     else
       epilogue_post<NOUT, NACC>(p, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane);
   }
@@ -458,11 +547,17 @@ struct ConvTsCfg {
   static constexpr int TAP_BYTES = NOUT * ROW_BYTES;
   static constexpr int W_BYTES = 9 * TAP_BYTES;
   static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
-  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? 32 * NOUT * 2 : 0;
-  static constexpr int OFF_STAGE = OFF_RING + TS_NSTAGE * SLOT_BYTES;
+  static constexpr int STAGE_BUFS = 2;
+  static constexpr int STAGE_BYTES = (EPI == EPI_HIDDEN) ? STAGE_BUFS * 32 * NOUT * 2 : 0;
+  // staging ring depth: the last layer (N = 16: 9 x 4 MMAs of ~9 cycles per row, no output staging) outruns a 4-slot
+  // ring by far and has the shared memory for a deep one
+  static constexpr int NSTAGE = (NOUT == 16) ? 10 : TS_NSTAGE;
+  static constexpr int OFF_STAGE = OFF_RING + NSTAGE * SLOT_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 256;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int BAR_BYTES = 512;
+  static_assert((2 * NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3) * 8 + 4 <= BAR_BYTES, "barrier block overflows");
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
   static_assert(TS_NACC * NOUT <= TS_A_COL0 && TS_A_COL0 + TS_NA * 96 <= 512, "TMEM plan does not fit 512 columns");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
@@ -471,14 +566,15 @@ template <int NOUT, int EPI>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   using Cfg = ConvTsCfg<NOUT, EPI>;
+  constexpr int NST = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
   uint8_t* ring = smem + Cfg::OFF_RING;
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // TMA landed a row in the staging ring
-  uint64_t* empty = full + TS_NSTAGE;                                 // loaders have copied it out
-  uint64_t* afull = empty + TS_NSTAGE;                                // the row's three shifted copies are in TMEM
+  uint64_t* empty = full + NST;                                 // loaders have copied it out
+  uint64_t* afull = empty + NST;                                // the row's three shifted copies are in TMEM
   uint64_t* aempty = afull + TS_NA;                                   // every MMA reading them has completed
   uint64_t* tfull = aempty + TS_NA;
   uint64_t* tempty = tfull + TS_NACC;
@@ -490,7 +586,7 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   griddep_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TS_NSTAGE; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 4);
     }
@@ -526,8 +622,8 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
-          const uint32_t slot = L % TS_NSTAGE;
-          mbar_wait(&empty[slot], ((L / TS_NSTAGE) & 1) ^ 1);
+          const uint32_t slot = L % NST;
+          mbar_wait(&empty[slot], ((L / NST) & 1) ^ 1);
           mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
           tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, y, c.b);
         }
@@ -595,8 +691,8 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       for (int y = c.ylo; y <= c.yhi; ++y, ++L) {
-        const uint32_t slot = L % TS_NSTAGE, as = L % TS_NA;
-        mbar_wait(&full[slot], (L / TS_NSTAGE) & 1);
+        const uint32_t slot = L % NST, as = L % TS_NA;
+        mbar_wait(&full[slot], (L / NST) & 1);
         mbar_wait(&aempty[as], ((L / TS_NA) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tile = ring_addr + slot * Cfg::SLOT_BYTES;
@@ -621,7 +717,7 @@ conv3x3_ts_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     uint32_t T = 0;
     if (EPI == EPI_HIDDEN)
       epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                     tmem_base, ew >> 2, warp & 3, lane, T);
+                                     tmem_base, ew >> 2, warp & 3, lane, T, 0, Cfg::STAGE_BUFS);
     else
       epilogue_post<NOUT, TS_NACC>(p, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane);
   }
@@ -655,7 +751,8 @@ struct ConvTs2Cfg {
   static constexpr int TAP_BYTES = (NOUT / 2) * ROW_BYTES;      // this CTA's half
   static constexpr int W_BYTES = 9 * TAP_BYTES;
   static constexpr int OFF_RING = round_up_c(W_BYTES, 1024);
-  static constexpr int STAGE_BYTES = 32 * NOUT * 2;
+  static constexpr int STAGE_BUFS = 2;
+  static constexpr int STAGE_BYTES = STAGE_BUFS * 32 * NOUT * 2;
   static constexpr int OFF_STAGE = OFF_RING + TS2_NSTAGE * SLOT_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 256;
@@ -835,7 +932,7 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int ew = warp - 6;
     uint32_t T = 0;
     epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                   tmem_base, ew >> 2, warp & 3, lane, T, tempty_c);
+                                   tmem_base, ew >> 2, warp & 3, lane, T, tempty_c, Cfg::STAGE_BUFS);
   }
   tc_fence_before();
   cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still signal or read it
@@ -1049,7 +1146,7 @@ conv3x3_ts_chain_kernel(const __grid_constant__ CUtensorMap map_ld0, const __gri
     for (int l = 0; l < cp.n_layers; ++l) {
       const float* bias = reinterpret_cast<const float*>(cp.weights0 + (size_t)l * HIDDEN_LAYER_STRIDE + Cfg::W_BYTES);
       epilogue_hidden<NOUT, TS_NACC>(p, ((l + 1) & 1) ? &map_st1 : &map_st0, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias,
-                                     tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, T);
+                                     tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, T, 0, Cfg::STAGE_BUFS);
       // epilogue_hidden ends with cp.async.bulk.wait_group 0 on the issuing lane: this warp's stores are complete
       __syncwarp();
       if (lane == 0) mbar_arrive(ldone);
