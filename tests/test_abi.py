@@ -90,3 +90,27 @@ def test_philox_known_answers(built):
         out = (C.c_uint32 * 4)()
         lib.psgla_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
         assert tuple(out) == want
+
+
+def test_next_pre_argument_errors_without_gpu(built):
+    """psgla_*_post_next validates the fused next-iteration pre descriptor on the host, before any CUDA call."""
+    L = built._lib
+    lib = L.lib()
+    shape = L.ImgShape(1, 3, 8, 8)
+    post = L.PostParams(1.0, 1.0, 0.0, 1.0)
+    pre = L.PreParams()
+    pre.alg = 7  # not a PSGLA_ALG_* value
+    fake = 0x1000  # never dereferenced: the descriptor is rejected first
+    bad_alg = L.NextPre(ctypes.pointer(pre), fake, fake, 1, 1, fake, fake)
+    rc = lib.psgla_dncnn_residual_post_next(20, fake, shape, fake, fake, 1 << 30, fake, ctypes.byref(post), fake, None, None, None,
+                                            ctypes.byref(bad_alg), None)
+    assert rc == -1 and b"alg=7" in lib.psgla_last_error()
+    pre.alg = 0
+    null_mask = L.NextPre(ctypes.pointer(pre), None, fake, 1, 1, fake, fake)
+    rc = lib.psgla_drunet_denoise_post_next(fake, shape, fake, fake, 1 << 30, fake, ctypes.byref(post), fake, None, None, None,
+                                            ctypes.byref(null_mask), None)
+    assert rc == -1 and b"psgla_next_pre" in lib.psgla_last_error()
+    bad_b = L.NextPre(ctypes.pointer(pre), fake, fake, 2, 1, fake, fake)  # mask_B must be 1 or B
+    rc = lib.psgla_dncnn_residual_post_next(20, fake, shape, fake, fake, 1 << 30, fake, ctypes.byref(post), fake, None, None, None,
+                                            ctypes.byref(bad_b), None)
+    assert rc == -1 and b"mask_B" in lib.psgla_last_error()
