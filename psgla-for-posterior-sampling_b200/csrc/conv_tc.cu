@@ -230,6 +230,135 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
   if (lane == 0) bulk_wait_group0();
 }
 
+// The same with the first residual tensor fetched by TMA (pair kernel, DRUNet's 64-channel residual blocks).  At 64 chains of
+// 320 x 480 the layer moves 3.8 GB and is HBM-bound (580 us at the measured copy bandwidth against 540 us of MMAs); per-thread
+// 16-byte loads of the residual reached only ~4 TB/s in total (950 us per layer, ncu).  Here lane 0 loads the warp's
+// 32-pixel residual box of its NEXT row straight into the staging box that row will use (the two boxes alternate), one row
+// ahead; the lanes then read-modify-write the box in shared memory and the TMA store ships it.  Box ownership: the load for
+// row n + 1 into box b' is issued after cp.async.bulk.wait_group.read 1, i.e. once the store of row n - 1 has finished
+// reading b'; generic writes precede the store by fence.proxy.async as before.
+template <int NOUT, int NACC_>
+__device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, const CUtensorMap* tmap_out,
+                                                       const CUtensorMap* tmap_res, uint8_t* stage, uint64_t* rbar,
+                                                       const float* bias_s, uint64_t* tfull, uint64_t* tempty,
+                                                       uint32_t tmem_base, int grp, int q4, int lane, uint32_t tempty_cluster) {
+  constexpr uint32_t BOX = 32 * NOUT * 2;
+  struct Iter {
+    int item, y, yend;
+    uint32_t T;
+    ItemCoord c;
+    bool done;
+  };
+  auto step = [&](Iter& r) {
+    ++r.y;
+    ++r.T;
+    if (r.y >= r.yend) {
+      r.item += gridDim.x;
+      if (r.item >= p.n_items) {
+        r.done = true;
+      } else {
+        r.c = decode_item(p, r.item);
+        r.y = r.c.y0;
+        r.yend = r.c.y0 + r.c.rcur;
+      }
+    }
+  };
+  auto settle = [&](Iter& r) {
+    while (!r.done && (int)(r.T & 1) != grp) step(r);
+  };
+  auto issue = [&](const Iter& r, uint32_t box) {  // lane 0: residual box of row r -> staging box `box`
+    const int xw = r.c.x0 + q4 * 32;
+    if (xw < p.W) {
+      mbar_expect_tx(&rbar[box], BOX);
+      tma_load_4d(stage + box * BOX, tmap_res, &rbar[box], 0, xw, r.y, r.c.b);
+    }
+  };
+  const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+  const bool relu = p.relu != 0;
+  if (lane == 0) {
+    tma_prefetch_desc(tmap_out);
+    tma_prefetch_desc(tmap_res);
+  }
+  griddep_wait();  // the residual tensor was written by an earlier kernel
+  Iter it;
+  it.item = blockIdx.x;
+  it.T = 0;
+  it.done = it.item >= p.n_items;
+  if (!it.done) {
+    it.c = decode_item(p, it.item);
+    it.y = it.c.y0;
+    it.yend = it.c.y0 + it.c.rcur;
+  }
+  settle(it);
+  uint32_t n = 0, cnt[2] = {0, 0};
+  if (!it.done && lane == 0) issue(it, 0);
+  while (!it.done) {
+    Iter nxt = it;
+    step(nxt);
+    settle(nxt);
+    const ItemCoord& c = it.c;
+    const int y = it.y;
+    const uint32_t T = it.T;
+    const uint32_t box = n & 1u;
+    const int xw = c.x0 + q4 * 32;
+    const bool row_has = xw < p.W;
+    const uint32_t acc = T % NACC_;
+    mbar_wait(&tfull[acc], (T / NACC_) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+    uint32_t v[NOUT];
+#pragma unroll
+    for (int h = 0; h < NOUT / 32; ++h) tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+    tmem_ld_wait();
+    tc_fence_before();
+    if (lane == 0) {
+      if (tempty_cluster)
+        mbar_arrive_remote(tempty_cluster + acc * 8u);
+      else
+        mbar_arrive(&tempty[acc]);
+    }
+    if (row_has) {
+      mbar_wait(&rbar[box], cnt[box] & 1u);  // this row's residual box has landed (pixels beyond W: zero fill)
+      ++cnt[box];
+    }
+    uint8_t* stage_cur = stage + box * BOX;
+    const uint32_t stage_row = smem_u32(stage_cur) + lane * (NOUT * 2);
+    const bool has_res2 = p.res2 != nullptr && xw + lane < p.W;
+    const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
+#pragma unroll
+    for (int j = 0; j < NOUT / 8; ++j) {
+      const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+      float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                    __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                    __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                    __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+      const uint32_t saddr = stage_row + ((uint32_t)(j ^ (lane & 7)) << 4);  // 128B swizzle: chunk ^= row & 7
+      if (row_has) add_bf16x8(f, ld_shared_v4(saddr));
+      if (has_res2) add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j));
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1], relu);
+      o.y = pack_bf16x2(f[2], f[3], relu);
+      o.z = pack_bf16x2(f[4], f[5], relu);
+      o.w = pack_bf16x2(f[6], f[7], relu);
+      st_shared_v4(saddr, o);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (row_has) tma_store_4d(tmap_out, stage_cur, 0, xw, y, c.b);
+      bulk_commit_group();
+      if (!nxt.done) {
+        bulk_wait_group_read1();  // the store of the previous row no longer reads the other box
+        issue(nxt, box ^ 1u);
+      }
+    }
+    __syncwarp();  // no lane touches the other box before lane 0 has seen it released
+    ++n;
+    it = nxt;
+  }
+  if (lane == 0) bulk_wait_group0();
+}
+
 // Last layer: the fused Langevin "post" step, fp32 NCHW (restoration_algorithms.py:238-262 / :115-135), optionally followed
 // by the next iteration's "pre" on the fresh iterate.
 // The layer is HBM-bound (128 B of activations in, ~70-140 B of fp32 state in and out per pixel) and its MMAs take only a few
@@ -756,15 +885,17 @@ struct ConvTs2Cfg {
   static constexpr int OFF_STAGE = OFF_RING + TS2_NSTAGE * SLOT_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGE + EPI_WARPS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 256;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
   static_assert(TS_NACC * NOUT <= TS_A_COL0 && TS_A_COL0 + TS_NA * 96 <= 512, "TMEM plan does not fit 512 columns");
-  static_assert((2 * TS2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3) * 8 + 4 <= 256, "barrier block overflows");
+  static_assert((2 * TS2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3 + 2 * EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier block overflows");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
 template <int NOUT>
 __global__ void __launch_bounds__(TS_THREADS, 1)
-conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
+                   const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
   using Cfg = ConvTs2Cfg<NOUT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -780,7 +911,8 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   uint64_t* wbar = tempty + TS_NACC;                                  // local: this CTA's half of the weights landed
   uint64_t* wready = wbar + 1;                                        // leader: the peer's half landed
   uint64_t* done = wready + 1;                                        // both (multicast): every MMA of the launch completed
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* rbar = done + 1;                                          // local: residual boxes (two per epilogue warp) landed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(rbar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -803,6 +935,7 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
     mbar_init(done, 1);
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -933,8 +1066,12 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
     const int ew = warp - 6;
     uint32_t T = 0;
-    epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                   tmem_base, ew >> 2, warp & 3, lane, T, tempty_c, Cfg::STAGE_BUFS);
+    if (p.res1 != nullptr)
+      epilogue_hidden_tmares<NOUT, TS_NACC>(p, &tmap_out, &tmap_res, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES,
+                                            rbar + 2 * ew, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, tempty_c);
+    else
+      epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
+                                     tmem_base, ew >> 2, warp & 3, lane, T, tempty_c, Cfg::STAGE_BUFS);
   }
   tc_fence_before();
   cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still signal or read it
@@ -1334,6 +1471,11 @@ static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStr
   if (rc) return rc;
   rc = get_act_tensor_map(&map_out, out_bf16, p.B, p.H, p.W, NOUT, 32);
   if (rc) return rc;
+  CUtensorMap map_res = map_out;  // unused without a residual input
+  if (p.res1) {
+    rc = get_act_tensor_map(&map_res, p.res1, p.B, p.H, p.W, NOUT, 32);
+    if (rc) return rc;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(TS_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -1361,7 +1503,7 @@ static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStr
   const int pairs = p.n_items / 2;
   cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
   if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: pair conv B=%d H=%d W=%d: R=%d items=%d grid=%u\n", p.B, p.H, p.W, p.R, p.n_items, cfg.gridDim.x);
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts2_kernel<NOUT>, map, map_out, p));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts2_kernel<NOUT>, map, map_out, map_res, p));
   return PSGLA_OK;
 }
 
