@@ -509,10 +509,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       const size_t off = (((size_t)c.b * p.Hout + yo) * p.Wout + xo) * p.Cout + (size_t)c.n0 * N_TILE;
       const bool has_res = valid && p.res1 != nullptr;
-      uint4 rr[16];
+      const bool has_res2 = valid && p.res2 != nullptr;  // U-Net skip: one layer per scale, same treatment
+      uint4 rr[16], rr2[16];
       if (has_res) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) rr[j] = *reinterpret_cast<const uint4*>(p.res1 + off + j * 8);
+      }
+      if (has_res2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rr2[j] = *reinterpret_cast<const uint4*>(p.res2 + off + j * 8);
       }
       mbar_wait(&tfull[acc], (T / CG_NACC) & 1);
       tc_fence_after();
@@ -541,7 +546,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 cg_add_bf16x8(f, rr[c4 * 4 + j]);
                 if (hb + 1 < NB) rr[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res1 + o + 128);
               }
-              if (p.res2) cg_add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + o));
+              if (has_res2) {
+                cg_add_bf16x8(f, rr2[c4 * 4 + j]);
+                if (hb + 1 < NB) rr2[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res2 + o + 128);
+              }
               uint4 w;
               w.x = cg_pack(f[0], f[1], relu);
               w.y = cg_pack(f[2], f[3], relu);

@@ -303,6 +303,14 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
     const int xw = c.x0 + q4 * 32;
     const bool row_has = xw < p.W;
     const uint32_t acc = T % NACC_;
+    // second residual tensor (U-Net skip, one layer per scale): per-thread loads, issued before the accumulator is awaited
+    const bool has_res2 = p.res2 != nullptr && xw + lane < p.W;
+    const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
+    uint4 rr2[NOUT / 8];
+    if (has_res2) {
+#pragma unroll
+      for (int j = 0; j < NOUT / 8; ++j) rr2[j] = *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j);
+    }
     mbar_wait(&tfull[acc], (T / NACC_) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
@@ -323,8 +331,6 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
     }
     uint8_t* stage_cur = stage + box * BOX;
     const uint32_t stage_row = smem_u32(stage_cur) + lane * (NOUT * 2);
-    const bool has_res2 = p.res2 != nullptr && xw + lane < p.W;
-    const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
 #pragma unroll
     for (int j = 0; j < NOUT / 8; ++j) {
       const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
@@ -334,7 +340,7 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
                     __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
       const uint32_t saddr = stage_row + ((uint32_t)(j ^ (lane & 7)) << 4);  // 128B swizzle: chunk ^= row & 7
       if (row_has) add_bf16x8(f, ld_shared_v4(saddr));
-      if (has_res2) add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j));
+      if (has_res2) add_bf16x8(f, rr2[j]);
       uint4 o;
       o.x = pack_bf16x2(f[0], f[1], relu);
       o.y = pack_bf16x2(f[2], f[3], relu);
