@@ -378,7 +378,7 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "gpu_launches": 20 * K,  # 20 conv launches; the Langevin pre / post steps live in the last layer's epilogue
         "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
                 "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
-        "roofline": {"kernel": "conv3x3_ts2_kernel<64> (CTA-pair tcgen05 implicit GEMM; 18 of the 21 launches per iteration)", "bound": "tensor",
+        "roofline": {"kernel": "conv3x3_ts2_kernel<64,false> (CTA-pair tcgen05 implicit GEMM; 18 of the 20 launches per iteration)", "bound": "tensor",
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms,

@@ -898,7 +898,9 @@ struct ConvTs2Cfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
-template <int NOUT>
+// RES: the layer has a residual input and fetches it by TMA (epilogue_hidden_tmares); a separate instantiation so that the
+// plain layers (all of DnCNN) keep their own register allocation and code (sharing one kernel cost them 5 %, ncu).
+template <int NOUT, bool RES>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
@@ -941,7 +943,8 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
     mbar_init(done, 1);
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
+    if (RES)
+      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1072,7 +1075,7 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
     const int ew = warp - 6;
     uint32_t T = 0;
-    if (p.res1 != nullptr)
+    if (RES)
       epilogue_hidden_tmares<NOUT, TS_NACC>(p, &tmap_out, &tmap_res, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES,
                                             rbar + 2 * ew, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, tempty_c);
     else
@@ -1469,8 +1472,8 @@ static void plan_items_pair(ConvParams* p, int n_clusters) {
   p->n_items = p->B * p->strips * p->row_blocks;
 }
 
-template <int NOUT>
-static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
+template <int NOUT, bool RES>
+static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
   using Cfg = ConvTs2Cfg<NOUT>;
   CUtensorMap map, map_out;
   int rc = get_act_tensor_map(&map, in, p.B, p.H, p.W, 64, BOX_W);
@@ -1497,11 +1500,11 @@ static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStr
   cfg.numAttrs = 2;
   static int max_clusters = 0;  // CTA pairs the device holds at once (one CTA per SM)
   if (!max_clusters) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts2_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts2_kernel<NOUT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
     int n = 0;
-    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv3x3_ts2_kernel<NOUT>, &cfg));
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv3x3_ts2_kernel<NOUT, RES>, &cfg));
     max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
     if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: conv3x3_ts2_kernel: %d co-resident CTA pairs (occupancy query %d)\n", max_clusters, n);
   }
@@ -1509,8 +1512,13 @@ static int launch_conv_ts2(const void* in, void* out_bf16, ConvParams p, cudaStr
   const int pairs = p.n_items / 2;
   cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
   if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: pair conv B=%d H=%d W=%d: R=%d items=%d grid=%u\n", p.B, p.H, p.W, p.R, p.n_items, cfg.gridDim.x);
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts2_kernel<NOUT>, map, map_out, map_res, p));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_ts2_kernel<NOUT, RES>, map, map_out, map_res, p));
   return PSGLA_OK;
+}
+
+template <int NOUT>
+static int launch_conv_ts2(const void* in, void* out_bf16, const ConvParams& p, cudaStream_t st) {
+  return p.res1 ? launch_conv_ts2_t<NOUT, true>(in, out_bf16, p, st) : launch_conv_ts2_t<NOUT, false>(in, out_bf16, p, st);
 }
 
 // PSGLA_CONV_PAIR=0 falls back to the single-CTA TS kernel (A/B runs)
