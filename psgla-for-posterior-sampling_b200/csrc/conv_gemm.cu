@@ -348,7 +348,9 @@ __device__ __forceinline__ CgItem cg_decode2(const CgParams& p, int item) {
   return c;
 }
 
-template <int N_TILE, bool REUSE>
+// RES2: a second residual tensor (U-Net skip, one layer per scale) is prefetched like the first; its own instantiation,
+// so that its 64 extra registers do not weigh on the other layers.
+template <int N_TILE, bool REUSE, bool RES2>
 __global__ void __launch_bounds__((CgCfg2<N_TILE, REUSE>::THREADS), 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const CgParams p) {
   using Cfg = CgCfg2<N_TILE, REUSE>;
@@ -509,15 +511,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       const size_t off = (((size_t)c.b * p.Hout + yo) * p.Wout + xo) * p.Cout + (size_t)c.n0 * N_TILE;
       const bool has_res = valid && p.res1 != nullptr;
-      const bool has_res2 = valid && p.res2 != nullptr;  // U-Net skip: one layer per scale, same treatment
-      uint4 rr[16], rr2[16];
+      const bool has_res2 = RES2 && valid && p.res2 != nullptr;
+      uint4 rr[16], rr2[RES2 ? 16 : 1];
       if (has_res) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) rr[j] = *reinterpret_cast<const uint4*>(p.res1 + off + j * 8);
       }
-      if (has_res2) {
+      if (RES2 && has_res2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rr2[j] = *reinterpret_cast<const uint4*>(p.res2 + off + j * 8);
+        for (int j = 0; j < 16; ++j) rr2[RES2 ? j : 0] = *reinterpret_cast<const uint4*>(p.res2 + off + j * 8);
       }
       mbar_wait(&tfull[acc], (T / CG_NACC) & 1);
       tc_fence_after();
@@ -546,9 +548,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 cg_add_bf16x8(f, rr[c4 * 4 + j]);
                 if (hb + 1 < NB) rr[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res1 + o + 128);
               }
-              if (has_res2) {
-                cg_add_bf16x8(f, rr2[c4 * 4 + j]);
-                if (hb + 1 < NB) rr2[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res2 + o + 128);
+              if (RES2 && has_res2) {
+                cg_add_bf16x8(f, rr2[RES2 ? c4 * 4 + j : 0]);
+                if (hb + 1 < NB) rr2[RES2 ? c4 * 4 + j : 0] = *reinterpret_cast<const uint4*>(p.res2 + o + 128);
               }
               uint4 w;
               w.x = cg_pack(f[0], f[1], relu);
@@ -628,8 +630,8 @@ static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParam
   return PSGLA_OK;
 }
 
-template <int N_TILE, bool REUSE>
-static int cg_launch2(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p, cudaStream_t st) {
+template <int N_TILE, bool REUSE, bool RES2>
+static int cg_launch2_t(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p, cudaStream_t st) {
   using Cfg = CgCfg2<N_TILE, REUSE>;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -646,18 +648,23 @@ static int cg_launch2(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p, 
   cfg.numAttrs = 2;
   static int max_clusters = 0;
   if (!max_clusters) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
     int n = 0;
-    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE>, &cfg));
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE, RES2>, &cfg));
     max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
   }
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int pairs = ((m_tiles + 1) / 2) * p.quads * p.n_tiles_n;
   p.n_items = 2 * pairs;
   cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<N_TILE, REUSE>, ma, mw, p));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<N_TILE, REUSE, RES2>, ma, mw, p));
   return PSGLA_OK;
+}
+
+template <int N_TILE, bool REUSE>
+static int cg_launch2(const CUtensorMap& ma, const CUtensorMap& mw, const CgParams& p, cudaStream_t st) {
+  return p.res2 ? cg_launch2_t<N_TILE, REUSE, true>(ma, mw, p, st) : cg_launch2_t<N_TILE, REUSE, false>(ma, mw, p, st);
 }
 
 // One layer.  in: bf16 NHWC [B][Hin][Win][Cin]; w: bf16 [taps][Cout][Cin]; out: bf16 NHWC (CONV3: same extent, DOWN2:
