@@ -10,6 +10,10 @@ namespace psgla {
 // validates a psgla_next_pre (inpainting "pre" of the next iteration, fused into the last layer's epilogue)
 int check_next_pre(const psgla_next_pre* next, const psgla_img_shape& shape);
 
+// Direction in which the next layer of a denoiser walks its work items: consecutive layers alternate, so that each starts on
+// the part of its input the previous layer wrote last (still in L2).  PSGLA_CONV_ALTERNATE=0 pins it to "forward".
+int next_layer_direction();
+
 // conv_tc.cu -- layers whose weights stay resident in shared memory
 void pack_conv3x3_swizzled(const float* w, int nout_real, int cin_real, int nout_pad, int cin_pad, uint8_t* dst);
 int conv64_hidden(const void* in, void* out, const uint8_t* w, const float* bias, int B, int H, int W, int relu,

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_api.cuh"
 #include "sm100.cuh"
 
 namespace psgla {
@@ -58,6 +59,7 @@ struct CgParams {
   int Hout, Wout;  // output tensor extent
   int PX, ROWS;    // tile = PX pixels x ROWS rows (PX * ROWS <= 128)
   int tiles_x, tiles_y, n_tiles_n, quads, n_items;
+  int reverse;  // pair kernels: walk the items back to front (alternates per layer, see conv_api.cuh)
   int relu;
   const __nv_bfloat16* res1;
   const __nv_bfloat16* res2;
@@ -331,6 +333,7 @@ struct CgCfg2 {
 };
 
 __device__ __forceinline__ CgItem cg_decode2(const CgParams& p, int item) {
+  if (p.reverse) item = p.n_items - 1 - item;  // items 2i, 2i+1 swap ranks and stay one pair
   CgItem c;
   const int inner = p.quads * p.n_tiles_n;
   const int rank = item & 1;
@@ -716,6 +719,7 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
     cg_reuse = (e && e[0] == '0') ? 0 : 1;
   }
   const bool reuse = pair && cg_reuse && mode == CG_CONV3 && p.PX == 128 && p.ROWS == 1;
+  p.reverse = pair ? next_layer_direction() : 0;
   p.n_tiles_n = Cout / n_tile;
   p.n_items = B * p.tiles_y * p.tiles_x * p.quads * p.n_tiles_n;
   p.relu = relu;

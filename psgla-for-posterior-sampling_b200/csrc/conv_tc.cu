@@ -88,6 +88,7 @@ struct ConvCfg {
 struct ConvParams {
   int B, H, W;
   int R, strips, row_blocks, n_items;
+  int reverse;  // walk the work items back to front (see decode_item)
   const uint8_t* weights;  // 9 taps, swizzled
   const float* bias;       // NOUT floats
   int relu;
@@ -117,7 +118,13 @@ static int set_next_pre(ConvParams* p, const psgla_next_pre* next);  // host: fi
 struct ItemCoord {
   int b, y0, rcur, x0, ylo, yhi;
 };
+// Items are dealt to the persistent CTAs in index order, so a layer finishes with the END of the activation tensor freshly
+// written -- and a 268 MB tensor (32 chains of 256 x 256 x 64 bf16) leaves roughly its last third in the 126 MB L2.  Consecutive
+// layers therefore walk the items in opposite directions (reverse = layer parity): each layer starts on what the previous one
+// wrote last and reads it from L2 instead of HBM.  (In the pair kernel items 2i and 2i + 1 swap ranks under the reversal and
+// still share chain and rows.)
 __device__ __forceinline__ ItemCoord decode_item(const ConvParams& p, int item) {
+  if (p.reverse) item = p.n_items - 1 - item;
   ItemCoord c;
   const int sx = item % p.strips;
   const int t = item / p.strips;
@@ -1664,6 +1671,16 @@ static int check_shape(const psgla_img_shape& s) {
   return PSGLA_OK;
 }
 
+// PSGLA_CONV_ALTERNATE=0: every layer walks its items front to back (A/B runs)
+static bool alternate_items() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSGLA_CONV_ALTERNATE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static ConvParams base_params(const psgla_img_shape& s, const uint8_t* packed, const LayerInfo& li) {
   ConvParams p{};
   p.B = s.B;
@@ -1738,6 +1755,7 @@ extern "C" int psgla_dncnn_residual_post_next(int depth, const void* packed_dev,
         const LayerInfo li = layer_info(depth, l);
         ConvParams pl = base_params(shape, packed, li);
         pl.relu = 1;
+        pl.reverse = alternate_items() ? (l & 1) : 0;
         rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[l & 1], pl, st) : launch_hidden64(cur, ws[l & 1], pl, st);
         if (rc) return rc;
         cur = ws[l & 1];
@@ -1755,6 +1773,7 @@ extern "C" int psgla_dncnn_residual_post_next(int depth, const void* packed_dev,
   p.base_scale = 1.0f;  // DnCNN is a residual denoiser: X+ = base + gain * R
   p.w_old = post->w_old;
   p.w_new = post->w_new;
+  p.reverse = alternate_items() ? ((depth - 1) & 1) : 0;
   rc = set_next_pre(&p, next);
   if (rc) return rc;
   return launch_last(cur, p, st);
@@ -1781,10 +1800,18 @@ void pack_conv3x3_swizzled(const float* w, int nout_real, int cin_real, int nout
       }
 }
 
+int next_layer_direction() {
+  static thread_local int dir = 0;
+  if (!alternate_items()) return 0;
+  dir ^= 1;
+  return dir;
+}
+
 int conv64_hidden(const void* in, void* out, const uint8_t* w, const float* bias, int B, int H, int W, int relu,
                   const void* res1, const void* res2, cudaStream_t st) {
   ConvParams p{};
   p.B = B, p.H = H, p.W = W;
+  p.reverse = next_layer_direction();
   p.weights = w;
   p.bias = bias;
   p.relu = relu;
