@@ -382,11 +382,11 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms,
-                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01i_conv3x3_ts2_full.txt): 273.7 MB read +
+                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01j_conv3x3_ts2_full.txt): 273.7 MB read +
                      # 218.4 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2.
                      # Same capture: tensor pipe active 75.2 % of the active cycles (single-CTA TS kernel: 62.4 %).
                      "traffic": 492.2e6 if (B == 32 and H == 256) else None,
-                     "traffic_source": "profiles/r01i_conv3x3_ts2_full.txt",
+                     "traffic_source": "profiles/r01j_conv3x3_ts2_full.txt",
                      "ncu_tensor_pipe_active_pct": 75.2},
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
