@@ -1,22 +1,24 @@
-// DnCNN conv3x3 layers as implicit GEMM on tcgen05 tensor cores (sm_100a), activations bf16 NHWC, fp32 accumulate.
+// 3x3 convolution layers with shared-memory-resident weights as implicit GEMM on tcgen05 tensor cores (sm_100a),
+// activations bf16 NHWC, fp32 accumulate: all of DnCNN and the 64-channel full-resolution layers of DRUNet.
 //
 // Replaces the cuDNN fp32 convolutions behind `denoiser.forward` (restoration_algorithms.py:238,
-// sampling_images.py:156; architecture: deepinv.models.DnCNN, see oracle/image_oracle.py).
+// sampling_images.py:156; architecture: deepinv.models.DnCNN / DRUNet, see oracle/image_oracle.py).
 //
-// Mapping (DESIGN.md "conv kernel"):
-//   GEMM view per output image row segment:  D[128 pixels x NOUT] = sum over 9 taps  A_tap[128 x CIN] * W_tap[NOUT x CIN]^T
-//   * A_tap is a *window* into input rows kept in shared memory: a work item walks down a 128-pixel-wide strip,
-//     every input row (130 pixels = 128 + halo, CIN channels, 128B- or 32B-swizzled by TMA) is loaded ONCE into a
-//     ring of NSTAGE slots and used by the 3 output rows around it; the horizontal tap offset dx is a +dx*row_bytes
-//     shift of the UMMA shared-memory descriptor's start address, the vertical tap dy picks the ring slot.
-//     TMA out-of-bounds zero fill provides the convolution's zero padding left/right; rows above/below the image
-//     are simply skipped (their taps contribute zero).
-//   * W (9 taps, bf16, K-major, pre-swizzled on the host) stays resident in shared memory for the CTA's lifetime.
-//   * accumulators live in TMEM (2 stages x NOUT columns); 4 epilogue warps read them with tcgen05.ld while the
-//     single MMA thread already works on the next row; one TMA thread keeps the ring full.
-//   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
-//   Epilogues: bias + ReLU -> bf16 NHWC (hidden layers); or the fused Langevin "post" step for the last layer:
-//   X+ = base + gain * (conv + bias), sample thinning and running E[X], E[X^2] (restoration_algorithms.py:238-262).
+// GEMM view per 128-pixel output row segment:  D[128 x NOUT] = sum over 9 taps  A_tap[128 x CIN] * W_tap[NOUT x CIN]^T.
+// A work item is a (chain, 128-pixel strip, block of R rows); every input row (130 pixels = 128 + halo, TMA out-of-bounds
+// zero fill = the convolution's padding) is loaded ONCE and serves the three output rows around it.  Kernels in this file:
+//   conv3x3_kernel<CIN,NOUT,EPI>   SS form: A_tap = window into the shared-memory row ring (tap dx = descriptor start + dx rows,
+//                                  tap dy = ring slot).  Used for the 3(16)-channel first layer; A/B variant for 64 channels.
+//   conv3x3_ts_kernel<NOUT,EPI>    TS form: four loader warps copy each row into TENSOR MEMORY three times (shifted by dx) and
+//                                  the MMAs take A from there (N/2 instead of 32 + N/4 cycles per MMA at N = 64).  Last layer
+//                                  (NOUT = 16, fused Langevin post / next pre epilogue); single-CTA form of the hidden layers.
+//   conv3x3_ts2_kernel<NOUT,RES>   the hidden layers: a CTA PAIR (cta_group::2, M = 256) on two adjacent strips, weights split
+//                                  32 / 32 output channels between the two shared memories; RES = residual input by TMA.
+//   conv3x3_ts_chain_kernel        experiment: 18 layers in one persistent launch with a grid barrier (off by default).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), [warps 2..5 = loaders (TS forms)], 8 epilogue warps
+// in two groups (TMEM -> bias / residual / ReLU -> bf16 -> swizzled staging box -> TMA store; or the fused Langevin step,
+// restoration_algorithms.py:238-262, for the last layer).  Consecutive layers walk their items in opposite directions
+// (ConvParams::reverse) so that each starts on what the previous one left in L2.  DESIGN.md section 4 has the measurements.
 #include <cuda_bf16.h>
 
 #include <algorithm>
