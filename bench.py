@@ -507,10 +507,10 @@ def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
         "config": {"workload": "random inpainting 50%%, sigma=1/255, PSGLA s=5/255 lambda=25 delta=s^2 alpha=1, DRUNet "
                                "(KAIR UNetRes 64/128/256/512, seeded random-init), %d chains/GPU of %dx%dx3" % (B, H, Wd),
                    "chains_per_gpu": B, "l2": "256 MiB flush between timed iterations"},
-        "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 69 * K,
+        "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 68 * K,
         "e2e": {"value": B * n_e2e * ws / (e2e_ms * 1e-3), "unit": "image-iterations/s", "iterations": n_e2e,
                 "h2d_bytes_per_step": int(3 * 3 * H * Wd * 4 / n_e2e), "d2h_bytes_per_step": int(B * 3 * H * Wd * 4 / n_e2e)},
-        "roofline": {"kernel": "whole iteration: 1 pre + 68 conv launches (CTA-pair kernels conv_gemm2_kernel<128|256> and "
+        "roofline": {"kernel": "whole iteration: 68 conv launches, the Langevin step in the last one (CTA-pair kernels conv_gemm2_kernel<128|256> and "
                                "conv3x3_ts2_kernel<64>; conv_gemm_kernel<64> for the 64-channel up-conv)",
                      "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": tflops / peaks["bf16_tflops"],
