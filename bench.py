@@ -319,7 +319,7 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
     conv_ms, _ = timer.total_ms()
     conv_launch_ms = conv_ms / (reps * 18)
 
-    # ---- the reference's own shape of run: ONE chain (launch-latency bound: 21 launches of ~8 us per iteration)
+    # ---- the reference's own shape of run: ONE chain (launch-latency bound: 20 launches of ~8 us per iteration)
     run1 = P.psgla_run(init, dg, den, n_iter=200, n_chains=1, chain_id0=rank, **kw)
     for i in range(20):
         run1.step(i)
