@@ -566,9 +566,26 @@ def _reference_available():
 def cpu_baseline_gmm2d(n_steps):
     use_ref = _reference_available()
     dt = _cpu_chain_worker(("psgla", "symetric_gaussians", (0.0, -2.0), n_steps, 0, use_ref))
-    return {"value": n_steps / dt, "unit": "chain-steps/s", "cores": 1, "kind": "reference" if use_ref else "port",
-            "sample": "1 chain x %d PSGLA steps, symetric_gaussians prior, y=(0,-2), float64 Python loop "
-                      "(the reference is single-threaded; independent chains scale with cores)" % n_steps}
+    out = {"value": n_steps / dt, "unit": "chain-steps/s", "cores": 1, "kind": "reference" if use_ref else "port",
+           "sample": "1 chain x %d PSGLA steps, symetric_gaussians prior, y=(0,-2), float64 Python loop "
+                     "(the reference is single-threaded; independent chains scale with cores)" % n_steps}
+    # the same algorithm as compiled C (oracle/gmm2d_oracle.c, float64, operation for operation): what one host core can do
+    # once the interpreter is out of the way -- the fairer yardstick for the kernel, reported beside the reference's own speed
+    try:
+        import numpy as np
+        from oracle import c_oracle, gmm2d_oracle as o
+        prior = o.gaussian_mixt_example("symetric_gaussians")
+        y = np.array([0.0, -2.0])
+        n_c = 4000000
+        c_oracle.run_chain("psgla", 1000, y, y, o.PSGLA_DELTA, np.eye(2), 1, prior, 1.0, o.PSGLA_ALPHA, seed=1)
+        t0 = time.perf_counter()
+        c_oracle.run_chain("psgla", n_c, y, y, o.PSGLA_DELTA, np.eye(2), 1, prior, 1.0, o.PSGLA_ALPHA, seed=0)
+        dt_c = time.perf_counter() - t0
+        out["c_port"] = {"value": n_c / dt_c, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+                         "sample": "1 chain x %d PSGLA steps, oracle/gmm2d_oracle.c (gcc -O2, float64, own Box-Muller stream)" % n_c}
+    except Exception as exc:  # noqa: BLE001
+        out["c_port"] = {"error": repr(exc)[:200]}
+    return out
 
 
 def cpu_baseline_image(args, n_iter=12):
