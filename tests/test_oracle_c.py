@@ -115,3 +115,34 @@ def test_c_run_chain_population_matches_the_numpy_oracle_population():
     se = ref.std(0) / np.sqrt(len(ref))
     assert (np.abs(got.mean(0) - ref.mean(0)) < 4 * se).all(), (got.mean(0), ref.mean(0), se)
     assert (np.abs(got.std(0) / ref.std(0) - 1) < 0.15).all(), (got.std(0), ref.std(0))
+
+
+@pytest.mark.reference
+def test_c_oracle_against_the_live_reference():
+    """In the build container: the UNMODIFIED reference (sampling_2D.py / utils_2D.py, loaded by oracle/ref_loader.py) run
+    next to the C restatement on the global NumPy stream -- denoiser on random points and 300-step trajectories of both
+    samplers for all three priors, plus a non-identity A with sigma != 1."""
+    from oracle import ref_loader
+    u2d = ref_loader.load_utils_2D()
+    s2d = ref_loader.load_sampling_2D()
+    rng = np.random.default_rng(3)
+    for name in o.PRIOR_NAMES:
+        mu, Sig, pi = u2d.gaussian_mixt_example(name)
+        prior = o.gaussian_mixt_example(name)
+        Dr = u2d.Theorical_MMSE(mu, Sig, pi)
+        for eps in (0.05, 0.3, 0.5):
+            for _ in range(40):
+                x = rng.uniform(-7, 7, size=2)
+                assert np.allclose(c.denoise(*prior, x, eps), Dr(x, eps), rtol=1e-11, atol=1e-12)
+        for y, A, sigma in ((np.array([0.0, -2.0]), np.eye(2), 1), (np.array([0.5, -1.0]), np.array([[2.0, 0.0], [0.3, 1.0]]), 1.5)):
+            N = 300
+            np.random.seed(11)
+            Xr = s2d.SnoPnP_ULA(N, y, y, 0.3, A, sigma, Dr, 2 / 3)
+            np.random.seed(11)
+            noise = np.random.randn(N - 1, 2)
+            assert np.allclose(c.snopnp_ula(N, y, y, 0.3, A, sigma, prior, 2 / 3, noise), Xr, rtol=1e-9, atol=1e-9)
+            np.random.seed(12)
+            Xr = s2d.PnP_ULA(N, y, y, 0.1, A, sigma, Dr, 0.5, 1.5)
+            np.random.seed(12)
+            noise = np.random.randn(N - 1, 2)
+            assert np.allclose(c.pnp_ula(N, y, y, 0.1, A, sigma, prior, 0.5, 1.5, noise), Xr, rtol=1e-9, atol=1e-9)
