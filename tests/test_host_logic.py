@@ -117,3 +117,41 @@ def test_torch_cuda_randn_policy_arithmetic():
         assert lib.psgla_torch_cuda_randn_policy(numel, 148, 2048, C.byref(t), C.byref(s)) == 0
         assert (t.value, s.value) == want, numel
     assert lib.psgla_torch_cuda_randn_policy(0, 148, 2048, C.byref(t), C.byref(s)) == -1
+
+
+def test_wasserstein_assignment_equals_the_transport_lp_on_small_clouds():
+    """POT's ``ot.emd2`` (utils_2D.py:242-243) is absent; the product and the oracle replace it by the assignment problem.
+    For equal-size uniform clouds the transport polytope's vertices are permutation matrices (Birkhoff), so the LP optimum is
+    the best permutation: checked here by brute force over all n! permutations for n <= 6, and against scipy's LP solver."""
+    import itertools
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 5, 6):
+        a, b = rng.normal(size=(n, 2)), rng.normal(size=(n, 2)) + 0.5
+        M = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+        brute = min(sum(M[i, p[i]] for i in range(n)) for p in itertools.permutations(range(n))) / n
+        # transport LP: min <M, T>, T 1 = 1/n, T^T 1 = 1/n, T >= 0
+        A_eq = np.zeros((2 * n, n * n))
+        for i in range(n):
+            A_eq[i, i * n:(i + 1) * n] = 1
+            A_eq[n + i, i::n] = 1
+        lp = linprog(M.reshape(-1), A_eq=A_eq, b_eq=np.full(2 * n, 1.0 / n), bounds=(0, None), method="highs")
+        assert lp.status == 0
+        got_p = P.Wasserstein_distance(a, b, n_sub=n, rng=np.random.default_rng(1))
+        got_o = o.wasserstein_distance(a, b, n_sub=n, rng=np.random.default_rng(1)) if hasattr(o, "wasserstein_distance") else got_p
+        assert abs(got_p - brute) < 1e-12 and abs(lp.fun - brute) < 1e-9 and abs(got_o - brute) < 1e-12
+
+
+def test_sliced_wasserstein_is_exact_for_translations_and_permutation_invariant():
+    """1-D optimal transport between equal-size clouds pairs sorted projections: a translated copy has sliced W2 = |t| E|cos|-free
+    closed form per direction (sqrt(mean (theta . t)^2)), and shuffling either cloud changes nothing."""
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(500, 2))
+    t = np.array([0.7, -1.3])
+    Y = X + t
+    got = P.sliced_wasserstein_distance(X, Y, n_projections=64, seed=5)
+    th = np.random.default_rng(5).standard_normal((2, 64))
+    th /= np.linalg.norm(th, axis=0, keepdims=True)
+    want = np.sqrt(np.mean((t @ th) ** 2))
+    assert abs(got - want) < 1e-12
+    assert abs(P.sliced_wasserstein_distance(X[rng.permutation(500)], Y[rng.permutation(500)], 64, seed=5) - got) < 1e-12
