@@ -186,3 +186,27 @@ def test_live_reference_bit_identical():
     for la, lb in zip(a, b):
         assert len(la) == len(lb)
         assert all(torch.equal(x, y) for x, y in zip(la, lb))
+
+
+def test_ssim_against_the_definition_window_by_window():
+    """skimage is absent, so the SSIM restatement (uniform_filter form) is checked against the definition itself: for every
+    interior pixel the 7x7 patches' means, UNBIASED variances and covariance (np.cov, ddof = 1 -- skimage's
+    use_sample_covariance=True default), S = (2 mu_x mu_y + C1)(2 cov + C2) / ((mu_x^2 + mu_y^2 + C1)(var_x + var_y + C2)),
+    averaged over the interior and then over channels (channel_axis = 2)."""
+    rng = np.random.default_rng(3)
+    a = rng.uniform(size=(19, 23, 3))
+    b = np.clip(a + 0.08 * rng.normal(size=a.shape), 0, 1)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    per_channel = []
+    for ch in range(3):
+        vals = []
+        for i in range(3, a.shape[0] - 3):
+            for j in range(3, a.shape[1] - 3):
+                pa = a[i - 3:i + 4, j - 3:j + 4, ch].reshape(-1)
+                pb = b[i - 3:i + 4, j - 3:j + 4, ch].reshape(-1)
+                cov = np.cov(pa, pb, ddof=1)
+                mx, my = pa.mean(), pb.mean()
+                vals.append((2 * mx * my + C1) * (2 * cov[0, 1] + C2) / ((mx * mx + my * my + C1) * (cov[0, 0] + cov[1, 1] + C2)))
+        per_channel.append(np.mean(vals))
+    assert io_.ssim(a, b) == pytest.approx(float(np.mean(per_channel)), abs=1e-12)
+    assert io_.psnr(a, b) == pytest.approx(10 * np.log10(1.0 / np.mean((a - b) ** 2)), abs=1e-12)
