@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PSGLA_ABI_VERSION 4
+#define PSGLA_ABI_VERSION 5
 
 enum {
   PSGLA_OK = 0,
@@ -295,6 +295,16 @@ int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, long long* cyc
 /* The same for a CTA pair: M256 x n x K16 MMAs (cta_group::2), mode 0: A from tensor memory, 1: from shared memory;
  * cycles_dev[n_pairs] = cycles the leader of each pair took for iters x 4 MMAs. */
 int psgla_selftest_mma_rate2(int mode, int n, int iters, int n_pairs, long long* cycles_dev, void* stream);
+
+/* FP32 issue-rate probe: the measured denominator of the 2D chain kernel's roofline.  num_sms x blocks_per_sm blocks of 256
+ * threads each run iters x 32 dependent-chain FMAs per thread (8 independent chains), mode 0: FFMA, mode 1: the packed FFMA2
+ * (fma.rn.f32x2).  out_dev: scratch of num_sms x blocks_per_sm x 256 floats (never written in practice); *flop_out (host) =
+ * flop the launch performs, so TFLOP/s = *flop_out / (CUDA-event time). */
+int psgla_selftest_fp32_rate(int mode, int iters, int blocks_per_sm, float* out_dev, double* flop_out, void* stream);
+/* The same for single instruction classes of the chain kernel's mix (csrc/selftest.cu lists the modes: 0 IMAD.WIDE.U32, 1
+ * IMAD.HI.U32, 2 IMAD, 3 LOP3, 4 MUFU.EX2, 5 I2FP, 6 FFMA, 7 MUFU.SIN, 8 IMAD.WIDE + FFMA 1:1); *ops_out = thread-level
+ * instructions of the probed class the launch executes (mode 8: of each of the two). */
+int psgla_selftest_pipe_rate(int mode, int iters, int blocks_per_sm, void* out_dev, double* ops_out, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -185,15 +185,12 @@ def blur_taps(l=4, blur_type="uniform", si=1.0):
     return h / np.sum(h)
 
 
-def make_deblurring(im_t, l=4, blur_type="uniform", si=1.0, sigma=1.0, seed_ip=0, device="cpu"):
-    """sampling_images.py:304-341.  Returns dict(A, AT, y, sigma2, init, data_grad, h)."""
-    sigma1 = sigma / 255.0
-    sigma2 = sigma1 ** 2
-    sigma2t = torch.tensor(sigma2, dtype=torch.float32, device=device)
-    h = blur_taps(l, blur_type, si)
+def blur_operators(h, l, C=3, device="cpu"):
+    """``A`` and ``AT`` exactly as sampling_images.py:313-330 builds them from the 1 x (2l+1) taps ``h``: circular pad l +
+    depthwise conv2d with flip(h^T h) resp. h^T h."""
+    h = np.asarray(h, dtype=np.float64).reshape(1, -1)
     h_ = np.dot(h.T, h)  # :313
     h_conv = np.copy(np.flip(h_))  # :314-315
-    C = im_t.shape[1]
     hconv = torch.from_numpy(h_conv).type(torch.FloatTensor).to(device)
     hcorr = torch.from_numpy(h_).type(torch.FloatTensor).to(device)
     ones = torch.ones(C, hconv.shape[0], hconv.shape[1]).to(device)
@@ -201,6 +198,22 @@ def make_deblurring(im_t, l=4, blur_type="uniform", si=1.0, sigma=1.0, seed_ip=0
     hcorr = hcorr.unsqueeze(0)[None, :, :, :] * ones[:, None, :, :]
     A = lambda x: F.conv2d(F.pad(x, [l, l, l, l], mode="circular"), hconv, groups=x.size(1), padding=0)  # :329
     AT = lambda x: F.conv2d(F.pad(x, [l, l, l, l], mode="circular"), hcorr, groups=x.size(1), padding=0)  # :330
+    return A, AT
+
+
+def deblur_data_grad(x, h, l, y, sigma2):
+    """``-AT(A(x) - y) / sigma2`` (sampling_images.py:338) in the reference's conv2d formulation, on x's device."""
+    A, AT = blur_operators(h, l, x.shape[1], x.device)
+    return -AT(A(x) - y) / torch.tensor(sigma2, dtype=torch.float32, device=x.device)
+
+
+def make_deblurring(im_t, l=4, blur_type="uniform", si=1.0, sigma=1.0, seed_ip=0, device="cpu"):
+    """sampling_images.py:304-341.  Returns dict(A, AT, y, sigma2, init, data_grad, h)."""
+    sigma1 = sigma / 255.0
+    sigma2 = sigma1 ** 2
+    sigma2t = torch.tensor(sigma2, dtype=torch.float32, device=device)
+    h = blur_taps(l, blur_type, si)
+    A, AT = blur_operators(h, l, im_t.shape[1], device)
     gen = torch.Generator(device=device)
     gen.manual_seed(seed_ip)
     y_t = A(im_t) + torch.normal(torch.zeros(*im_t.size()).to(device),

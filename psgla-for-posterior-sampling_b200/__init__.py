@@ -8,6 +8,8 @@ directory name carries the reference's name and is not a Python identifier).
 from . import _lib  # noqa: F401
 from . import dist  # noqa: F401
 from . import metrics  # noqa: F401
+from . import image_set  # noqa: F401
+from .image_set import load_image, run_image_set  # noqa: F401
 from .metrics import posterior_summary, psnr_ssim  # noqa: F401
 from .denoisers import (DRUNET_KEYS, DRUNet, DnCNN, lipschitz_dncnn_state_dict, random_dncnn_state_dict,  # noqa: F401
                         random_drunet_state_dict)  # noqa: F401

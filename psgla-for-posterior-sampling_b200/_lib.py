@@ -100,6 +100,8 @@ SIGNATURES = {
     "psgla_convg_layer": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "psgla_selftest_mma_rate": (_int, [_int, _int, _int, _int, _vp, _vp]),
     "psgla_selftest_mma_rate2": (_int, [_int, _int, _int, _int, _vp, _vp]),
+    "psgla_selftest_fp32_rate": (_int, [_int, _int, _int, _vp, C.POINTER(C.c_double), _vp]),
+    "psgla_selftest_pipe_rate": (_int, [_int, _int, _int, _vp, C.POINTER(C.c_double), _vp]),
 }
 
 _lock = threading.Lock()

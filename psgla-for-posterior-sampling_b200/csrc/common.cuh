@@ -1,6 +1,7 @@
 // Shared device/host helpers of libpsgla_b200: error plumbing, Philox4x32-10, Box-Muller.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -26,17 +27,25 @@ int set_error(int code, const char* fmt, ...);
     if (!(cond)) return ::psgla::set_error(PSGLA_E_BADARG, __VA_ARGS__); \
   } while (0)
 
-inline int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
-  }
-  return cached;
+// Per-device caches: the library may be driven on several GPUs from one process (the Python layer takes device=...), so
+// nothing that depends on the device is cached process-wide.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
 }
-
+inline int num_sms() {
+  static std::atomic<int> cached[kMaxDevices];
+  const int dev = current_device();
+  int v = (dev >= 0 && dev < kMaxDevices) ? cached[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    if (dev >= 0 && dev < kMaxDevices) cached[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 // ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
 // counter = (c0, c1, c2, c3), key = (seed_lo, seed_hi).  Library convention:
 //   2D   : c0,c1 = (global step >> 1) as 64 bit, c2,c3 = global chain id

@@ -613,10 +613,11 @@ static int cg_cached_map(CUtensorMap* map, const CgMapKey& key, int rank, const 
 template <int N_TILE, bool TS>
 static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParams& p, cudaStream_t st) {
   using Cfg = CgCfg<N_TILE, TS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   cudaLaunchConfig_t cfg{};

@@ -1401,11 +1401,12 @@ static int launch_conv(const void* in, void* out_bf16, ConvParams p, cudaStream_
   } else {
     map_out = map;  // unused by the fused-post epilogue
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_kernel<CIN, NOUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   plan_items(&p);
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
@@ -1435,11 +1436,12 @@ static int launch_conv_ts(const void* in, void* out_bf16, ConvParams p, cudaStre
   } else {
     map_out = map;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts_kernel<NOUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   plan_items(&p);
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
@@ -1567,10 +1569,11 @@ static int launch_hidden_chain(void* buf0, void* buf1, int n_layers, const uint8
   if (!rc) rc = get_act_tensor_map(&st0, buf0, p.B, p.H, p.W, 64, 32);
   if (!rc) rc = get_act_tensor_map(&st1, buf1, p.B, p.H, p.W, 64, 32);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   plan_items(&p);
   p.relu = 1;
@@ -1981,10 +1984,11 @@ extern "C" int psgla_selftest_umma(const void* a_dev, const void* b_dev, float* 
     if (r != CUDA_SUCCESS) return set_error(PSGLA_E_BADARG, "tensor map B: CUresult %d", (int)r);
   }
   const int smem = 30 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, d_dev, row_shift, mode);
   PSGLA_CUDA_TRY(cudaGetLastError());
@@ -2267,11 +2271,12 @@ extern "C" int psgla_selftest_mma_rate2(int mode, int n, int iters, int n_pairs,
   PSGLA_REQUIRE(cycles_dev && (mode == 0 || mode == 1) && n >= 32 && n <= 256 && n % 32 == 0 && iters > 0 && n_pairs > 0,
                 "psgla_selftest_mma_rate2: bad argument");
   const int smem = 54 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
@@ -2297,8 +2302,9 @@ extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, lon
                 "psgla_selftest_mma_rate: bad argument");
   PSGLA_REQUIRE(mode < 3 || n <= 128, "alternating-accumulator modes need n <= 128");
   const int smem = 54 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -2307,7 +2313,7 @@ extern "C" int psgla_selftest_mma_rate(int mode, int n, int iters, int grid, lon
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {

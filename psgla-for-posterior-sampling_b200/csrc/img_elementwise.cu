@@ -552,10 +552,11 @@ template <bool FULL, int L>
 static int launch_blur_t(const PreArgs& a, psgla_img_shape s, const float* x, const float* y, int y_B, const float* noise,
                          float* out, void* den_in, cudaStream_t st) {
   constexpr size_t smem = BlurCfg<FULL, L>::SMEM;
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (smem > 48 * 1024 && !(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(blur_kernel_t<FULL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int tiles = ((s.W + BT - 1) / BT) * ((s.H + BT - 1) / BT);
   blur_kernel_t<FULL, L><<<dim3(tiles, s.B), 256, smem, st>>>(a, s.B, s.H, s.W, x, y, y_B, noise, out, (__nv_bfloat16*)den_in);

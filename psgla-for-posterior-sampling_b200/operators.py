@@ -12,7 +12,6 @@ import ctypes as C
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 
@@ -71,22 +70,17 @@ class DeblurDataGrad:
         self.sigma2 = float(sigma2)
         self._taps_c = (C.c_float * (2 * self.l + 1))(*[float(np.float32(v)) for v in self.h1d])
 
-    def _kernel(self, x):
-        h2 = torch.from_numpy(np.outer(self.h1d, self.h1d)).type(torch.FloatTensor).to(x.device)
-        return h2[None, None].repeat(x.size(1), 1, 1, 1)
-
     def A(self, x):
-        """The blur itself.  CUDA tensors go through the library's stencil kernel; CPU tensors follow the
-        reference's conv2d formulation (only so that the reference's own samplers can consume this object)."""
-        if x.is_cuda:
-            x = x.to(torch.float32).contiguous()
-            out = torch.empty_like(x)
-            with torch.cuda.device(x.device):
-                _lib.check(_lib.lib().psgla_img_blur(_shape_of(x), _lib.ptr(x), self._taps_c, self.l, _lib.ptr(out),
-                                                     _lib.stream_ptr(x.device)), "psgla_img_blur")
-            return out
-        l = self.l
-        return F.conv2d(F.pad(x, [l, l, l, l], mode="circular"), self._kernel(x), groups=x.size(1), padding=0)
+        """The blur itself: the library's circular separable stencil kernel (CUDA tensors only -- there is no CPU path; the
+        reference's pad-circular + depthwise ``conv2d`` formulation is restated in the test infrastructure, not here)."""
+        if not x.is_cuda:
+            raise RuntimeError("DeblurDataGrad needs CUDA tensors: there is no CPU path")
+        x = x.to(torch.float32).contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().psgla_img_blur(_shape_of(x), _lib.ptr(x), self._taps_c, self.l, _lib.ptr(out),
+                                                 _lib.stream_ptr(x.device)), "psgla_img_blur")
+        return out
 
     AT = A
 

@@ -14,6 +14,12 @@ Extra keyword-only arguments:
   n_chains       run that many independent chains of the same problem (init broadcast); outputs gain a leading
                  chain axis
   chain_id0      global id of the first chain (Philox subsequence) when chains are sharded over GPUs
+  store          "all" (default, the reference's behaviour: every thinned sample and every window mean is kept, N=10^4 /
+                 n_inter=10 is 1 000 samples + 909 x 2 window moments per chain) or "stats" (statistics-only: no sample is
+                 stored -- ``Xlist`` comes back empty -- and the window means are folded into their running average on the
+                 device, so ``Xlist_mmse`` / ``Xlist_mmse2`` hold ONE tensor each: the mean over windows the reference's
+                 post-processing forms anyway, sampling_images.py:427,436).  What batched runs (64 chains per image) need:
+                 memory independent of n_iter.
 The data term must be an ``InpaintingDataGrad`` / ``DeblurDataGrad`` and the denoiser a ``psgla_b200.DnCNN``
 (``prior_grad`` a ``PriorGrad`` wrapping one); opaque callables raise ``TypeError`` -- there is no eager fallback.
 """
@@ -40,8 +46,12 @@ def _f(v):
 class _Run:
     """State shared by both samplers: buffers, thinning, running moments (restoration_algorithms.py:118-144)."""
 
-    def __init__(self, init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0):
+    def __init__(self, init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0,
+                 store="all"):
         _lib.require_cuda()
+        if store not in ("all", "stats"):
+            raise ValueError("store must be 'all' or 'stats'")
+        self.store = store
         if not isinstance(data_grad, (InpaintingDataGrad, DeblurDataGrad)):
             raise TypeError("data_grad must be an InpaintingDataGrad or DeblurDataGrad (structured callable); an opaque "
                             "callable cannot be fused into the CUDA kernels and there is no eager fallback")
@@ -57,6 +67,9 @@ class _Run:
         x = init.detach().to(torch.float32)
         if x.dim() == 3:
             x = x[None]
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("init must be a [B,3,H,W] (or [3,H,W]) colour image batch, got %s: the kernels index three "
+                             "planes per chain (the reference's --grayscale runs are out of scope)" % (tuple(init.shape),))
         self.squeeze = n_chains is None and x.shape[0] == 1
         B = int(n_chains) if n_chains is not None else int(x.shape[0])
         self.X = x.expand(B, -1, -1, -1).contiguous().clone() if x.shape[0] != B else x.contiguous().clone()
@@ -68,7 +81,10 @@ class _Run:
         if self.n_inter < 1:
             raise ZeroDivisionError("integer modulo by zero (n_inter must be >= 1, as in the reference)")
         n_samples = (self.n_iter + self.n_inter - 1) // self.n_inter
-        self.samples = torch.empty((max(n_samples, 1),) + tuple(self.X.shape), dtype=torch.float32, device=self.device)
+        self.samples = None
+        if store == "all":
+            self.samples = torch.empty((max(n_samples, 1),) + tuple(self.X.shape), dtype=torch.float32, device=self.device)
+        self.n_windows, self.win_sum, self.win_sum2 = 0, None, None  # statistics-only: running sums of the window means
         self.mean = torch.zeros_like(self.X)
         self.mean2 = torch.zeros_like(self.X)
         # closed windows are copied into storage reserved in chunks, so that no allocator call (a device-wide
@@ -102,12 +118,25 @@ class _Run:
         if noise is not None and tuple(noise.shape[1:]) != tuple(self.X.shape) and not (
                 self.X.shape[0] == 1 and tuple(noise.shape[1:]) == tuple(self.X.shape[1:])):
             raise ValueError("noise must have shape (n_iter, *init.shape)")
+        if noise is not None and noise.shape[0] < self.n_iter:
+            raise ValueError("noise holds %d draws but n_iter = %d" % (noise.shape[0], self.n_iter))
+        H, W = int(self.X.shape[2]), int(self.X.shape[3])
+
+        def operand(t, what, channels):
+            t = t.to(self.device)
+            if t.dim() == 3:
+                t = t[None]
+            if t.dim() != 4 or t.shape[0] not in (1, B) or t.shape[1] not in channels or tuple(t.shape[2:]) != (H, W):
+                raise ValueError("%s has shape %s; expected [1 or %d, %s, %d, %d] to match init" %
+                                 (what, tuple(t.shape), B, "/".join(str(c) for c in channels), H, W))
+            return t.expand(-1, 3, -1, -1).contiguous()
+
         if isinstance(data_grad, DeblurDataGrad):
-            self.y = data_grad.y.to(self.device)
+            self.y = operand(data_grad.y, "the blurred observation y", (3,))
             self.mask = None
         else:
-            self.y = data_grad.y.to(self.device).expand(-1, 3, -1, -1).contiguous()
-            self.mask = data_grad.mask.to(self.device).expand(-1, 3, -1, -1).contiguous()
+            self.y = operand(data_grad.y, "the observation y", (1, 3))
+            self.mask = operand(data_grad.mask, "the mask", (1, 3))
 
     def configure(self, pre, gain, base_scale=1.0):
         self.pre_params, self.gain, self.base_scale = pre, float(gain), float(base_scale)
@@ -163,7 +192,7 @@ class _Run:
     def post(self, i, gain, next_iteration=None):
         k = self.iter_mmse
         post = _lib.PostParams(float(gain), self.base_scale, float(np.float32(k / (k + 1))), float(np.float32(1 / (k + 1))))
-        sample = self.samples[i // self.n_inter] if i % self.n_inter == 0 else None
+        sample = self.samples[i // self.n_inter] if (self.samples is not None and i % self.n_inter == 0) else None
         nxt = None
         if next_iteration is not None:
             if self.noise is not None or self.gen is not None:
@@ -178,6 +207,16 @@ class _Run:
         # window bookkeeping exactly as restoration_algorithms.py:128-144 / :255-271
         if self.iter_mmse <= self.n_inter_mmse - 1:
             self.iter_mmse += 1
+        elif self.store == "stats":
+            # statistics-only: fold the closed window into the running sums instead of keeping it (the reference's tail
+            # averages the window means anyway, sampling_images.py:427,436); Xlist_mmse / Xlist_mmse2 come from finish()
+            if self.win_sum is None:
+                self.win_sum, self.win_sum2 = self.mean.clone(), self.mean2.clone()
+            else:
+                self.win_sum.add_(self.mean)
+                self.win_sum2.add_(self.mean2)
+            self.n_windows += 1
+            self.iter_mmse = 0
         else:
             if self._win_chunk is None or self._win_used == self._win_chunk.shape[0]:
                 per_window = 2 * self.mean.numel() * 4
@@ -194,6 +233,15 @@ class _Run:
             self.iter_mmse = 0  # the next update has w_old = 0, which restarts the window without a memset
 
 
+    def finish(self):
+        """The reference's return triple.  Statistics-only runs return ([], [mean of the window means], [mean of the window
+        second moments]) -- one tensor each, empty lists when no window closed."""
+        if self.store == "stats" and self.n_windows:
+            self.Xlist_mmse = [self._out(self.win_sum / self.n_windows)]
+            self.Xlist_mmse2 = [self._out(self.win_sum2 / self.n_windows)]
+        return self.Xlist, self.Xlist_mmse, self.Xlist_mmse2
+
+
 def _save_online(path, name, i, run, extra):
     # restoration_algorithms.py:146-158 / :273-283 (the PNG previews need matplotlib and are not reproduced)
     d = {"Samples": run.Xlist, "Mmse": run.Xlist_mmse, "Mmse2": run.Xlist_mmse2, "n_iter": run.n_iter}
@@ -202,10 +250,10 @@ def _save_online(path, name, i, run, extra):
 
 
 def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
-              n_inter_mmse=1000, seed=None, *, noise=None, rng=None, n_chains=None, chain_id0=0):
+              n_inter_mmse=1000, seed=None, *, noise=None, rng=None, n_chains=None, chain_id0=0, store="all"):
     """The stepping object behind ``psgla``: ``run.step(i)`` issues iteration i (one "pre" launch + the DnCNN layer
     chain); ``run.Xlist`` / ``run.Xlist_mmse`` / ``run.Xlist_mmse2`` are the reference's three lists."""
-    run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    run = _Run(init, data_grad, denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0, store)
     delta32 = float(np.float32(delta))
     sig32 = float(np.float32(sig_float))
     pre = _lib.PreParams()
@@ -224,26 +272,27 @@ def psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4
 
 def psgla(init, data_grad, denoiser, alpha, lambd, sig_float=0.0055, delta=4e-5, n_iter=5000, n_inter=1000,
           n_inter_mmse=1000, seed=None, device=None, path=None, save_images_online=False, name=None, *, noise=None,
-          rng=None, n_chains=None, chain_id0=0):
+          rng=None, n_chains=None, chain_id0=0, store="all"):
     """PSGLA (restoration_algorithms.py:163-285):  Y = X + (delta/lambd) data_grad(X) + sqrt(2) sig Z;
     X = (1 - alpha) Y + alpha D(Y).  Returns (Xlist, Xlist_mmse, Xlist_mmse2)."""
     run = psgla_run(init, data_grad, denoiser, alpha, lambd, sig_float, delta, n_iter, n_inter, n_inter_mmse, seed,
-                    noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0)
+                    noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0, store=store)
     print("delta = {}, sigma = {}".format(delta, sig_float))
     K = int(run.n_iter / 10)
     for i in range(run.n_iter):
         run.step(i)
         if save_images_online and i % K == 0:  # ZeroDivisionError for n_iter < 10 with the flag, as in the reference (:246)
             _save_online(path, name, i, run, {"lambda": lambd, "delta": delta})
-    return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
+    return run.finish()
 
 
 def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
-               c_min=-1, c_max=2, *, noise=None, rng=None, n_chains=None, chain_id0=0):
+               c_min=-1, c_max=2, *, noise=None, rng=None, n_chains=None, chain_id0=0, store="all"):
     """The stepping object behind ``pnpula`` (see ``psgla_run``)."""
     if not isinstance(prior_grad, PriorGrad):
         raise TypeError("prior_grad must be a PriorGrad(denoiser, alpha, s1, s2) structured callable")
-    run = _Run(init, data_grad, prior_grad.denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0)
+    run = _Run(init, data_grad, prior_grad.denoiser, n_iter, n_inter, n_inter_mmse, seed, noise, rng, n_chains, chain_id0,
+               store)
     delta_f, lambd_f = _f(delta), _f(lambd)
     pre = _lib.PreParams()
     pre.alg = _lib.ALG_PNPULA
@@ -262,18 +311,18 @@ def pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1
 
 def pnpula(init, data_grad, prior_grad, delta, lambd, n_iter=5000, n_inter=1000, n_inter_mmse=1000, seed=None,
            device=None, c_min=-1, c_max=2, path=None, save_images_online=False, name=None, *, noise=None, rng=None,
-           n_chains=None, chain_id0=0):
+           n_chains=None, chain_id0=0, store="all"):
     """PnP-ULA (restoration_algorithms.py:38-160):
     X+ = X + delta (prior_grad(X) - (X - proj_[c_min,c_max] X)/lambd + data_grad(X)) + sqrt(2 delta) Z."""
     run = pnpula_run(init, data_grad, prior_grad, delta, lambd, n_iter, n_inter, n_inter_mmse, seed, c_min, c_max,
-                     noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0)
+                     noise=noise, rng=rng, n_chains=n_chains, chain_id0=chain_id0, store=store)
     print("delta = {}".format(delta.float() if isinstance(delta, torch.Tensor) else delta))
     K = int(run.n_iter / 10)
     for i in range(run.n_iter):
         run.step(i)
         if save_images_online and i % K == 0:
             _save_online(path, name, i, run, {"c_min": c_min, "c_max": c_max, "lambda": lambd, "delta": delta})
-    return run.Xlist, run.Xlist_mmse, run.Xlist_mmse2
+    return run.finish()
 
 
 pnp_ula = pnpula

@@ -32,7 +32,7 @@ def test_library_exports_every_symbol(built):
     handle = ctypes.CDLL(built._lib.LIB_PATH)
     for fn in _header_functions():
         assert hasattr(handle, fn), fn
-    assert handle.psgla_abi_version() == 4
+    assert handle.psgla_abi_version() == 5
 
 
 def test_struct_sizes_match_header(built):

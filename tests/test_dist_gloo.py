@@ -46,3 +46,47 @@ def test_shard_gather_world2(tmp_path):
     want = np.stack([np.sin(ids), np.cos(ids)], 1)
     assert np.allclose(got[:-2].reshape(n_total, 2), want)
     assert np.allclose(got[-2:], want.mean(0))
+
+
+def _fake_sample(index, im):
+    """Stands in for the CUDA sampler: a row that depends only on the image and its GLOBAL index (what the real path
+    guarantees through chain_id0 = index * n_chains)."""
+    import psgla_b200 as P
+    row = torch.zeros(len(P.image_set.ROW_FIELDS), dtype=torch.float64)
+    row[0] = index
+    row[1] = float(im.double().mean()) + index
+    row[2] = float(im.double().std())
+    row[-2], row[-1] = im.shape[-2], im.shape[-1]
+    return row, None
+
+
+def _set_worker(rank, ws, port, n_images, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    import psgla_b200 as P
+    P.dist.init_from_env(backend="gloo")
+    g = torch.Generator().manual_seed(0)
+    images = [torch.rand(3, 8 + i, 10, generator=g) for i in range(n_images)]  # ragged sizes, same list on every rank
+    assert P.image_set.deal_round_robin(n_images, rank, ws) == list(range(rank, n_images, ws))
+    res = P.run_image_set(images, _sample=_fake_sample)
+    if rank == 0:
+        np.save(out_path, np.array([[d["index"], d["psnr_mmse"], d["ssim_mmse"], d["H"], d["W"]] for d in res]))
+    else:
+        assert res is None
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_image_set_round_robin_is_world_size_invariant(tmp_path):
+    """run_image_set's host logic (deal -> per-image rows -> gather -> order) at world size 2 and 3 over gloo against the single
+    process: 5 images (ragged deal 3 + 2, and 2 + 2 + 1), more ranks than images is covered by n_images = 1."""
+    import psgla_b200 as P
+    for n_images in (5, 1):
+        g = torch.Generator().manual_seed(0)
+        images = [torch.rand(3, 8 + i, 10, generator=g) for i in range(n_images)]
+        solo = P.run_image_set(images, _sample=_fake_sample)
+        want = np.array([[d["index"], d["psnr_mmse"], d["ssim_mmse"], d["H"], d["W"]] for d in solo])
+        assert [d["index"] for d in solo] == list(range(n_images))
+        for ws in (2, 3):
+            out = str(tmp_path / ("s%d_%d.npy" % (n_images, ws)))
+            mp.spawn(_set_worker, args=(ws, _free_port(), n_images, out), nprocs=ws, join=True)
+            assert np.array_equal(np.load(out), want)

@@ -137,6 +137,35 @@ def test_philox_noise_is_standard_normal_and_replayable():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("alg", ["psgla", "pnp_ula"])
+@pytest.mark.parametrize("name,A", [("symetric_gaussians", np.eye(2)), ("disymmetric_gaussians", np.eye(2)), ("cross", np.eye(2)),
+                                    ("symetric_gaussians", np.array([[1.0, 0.3], [-0.2, 0.8]]))])
+def test_lean_kernel_and_every_launch_geometry_equal_the_replayed_stream(name, A, alg, monkeypatch):
+    """The throughput path (csrc/gmm2d.cu: the register-lean one-chain-per-thread kernel with 4 Philox blocks per round, its
+    constants-structure specialisations STRUCT 0 / 1 / 2, the packed FFMA2 variants, the dynamically scheduled and the
+    wave-split launches) must consume exactly the library's Philox stream and do the general kernel's arithmetic: 45 steps
+    from an odd global step (1 lead step + 5 lean rounds of 8 + 4 tail steps) == the replay of the dumped draws, bit for bit."""
+    lib = P._lib.lib()
+    C, n, off = 3000, 45, 3
+    z = torch.empty(n, C, 2, device="cuda")
+    P._lib.check(lib.psgla_gmm2d_noise(z.data_ptr(), C, 5, n, off, 77, None), "noise")
+    D = P.Theorical_MMSE(*P.gaussian_mixt_example(name))
+    y = np.array([0.0, -2.0])
+    prm = dict(delta=0.3, alpha=2 / 3, epsilon=1.0) if alg == "psgla" else dict(delta=0.1, alpha=1.5, epsilon=0.5)
+    kw = dict(y=y, A=A, sigma=1, denoiser=D, n_chains=C, **prm)
+    want, _ = P.run_chains(alg, n, noise=z, **kw)
+    for geom in ("", "4,1,128,0,0", "1,4,32,0,1", "2,2,128,1,1", "4,1,128,1,0", "4,64,16,0,2", "2,64,16,0,2", "8,32,32,0,2",
+                 "4,32,32,1,2"):
+        monkeypatch.setenv("PSGLA_GMM_GEOM", geom)
+        got, _ = P.run_chains(alg, n, seed=77, chain_id0=5, philox_offset=off, **kw)
+        assert torch.equal(got, want), geom
+    monkeypatch.setenv("PSGLA_GMM_GEOM", "")
+    for cap in ("0", "1"):  # the structure specialisation switched off / capped: same bits
+        monkeypatch.setenv("PSGLA_GMM_STRUCT", cap)
+        got, _ = P.run_chains(alg, n, seed=77, chain_id0=5, philox_offset=off, **kw)
+        assert torch.equal(got, want), cap
+
+
 def test_sharding_and_segmentation_invariance():
     """Chain i's result depends only on (seed, global id, step index): not on the shard or on how steps are split."""
     mu, Sig, pi = P.gaussian_mixt_example("cross")

@@ -96,7 +96,7 @@ def test_blur_against_reference_formulation():
         h = P.blur_taps(l, bt, 1.3).reshape(-1)
         op = P.DeblurDataGrad(h, l, torch.zeros_like(im), 1.0)
         got = op.A(im)
-        want = op.A(im.cpu()).cuda()  # the reference's pad-circular + depthwise conv2d formulation (sampling_images.py:329)
+        want = io_.blur_operators(h, l, 3, "cuda")[0](im)  # the reference's pad-circular + depthwise conv2d (sampling_images.py:329)
         assert (got - want).abs().max().item() < 1e-5
 
 
@@ -149,8 +149,8 @@ def test_pre_deblur_against_oracle(H, W, l, bt):
     prm = io_.resolve_params("psgla")
     pre = P._lib.PreParams()
     pre.alg, pre.gain_data, pre.noise_scale = 0, (prm["delta"] / prm["lambd"]) / dd.sigma2, float(np.sqrt(2) * prm["s"])
-    ref_op = P.DeblurDataGrad(dd.h1d, l, y.cpu(), dd.sigma2)  # CPU tensors -> the reference's conv2d formulation
-    want = (x.cpu() + (prm["delta"] / prm["lambd"]) * ref_op(x.cpu()) + float(np.sqrt(2) * prm["s"]) * z.cpu()).cuda()
+    grad = io_.deblur_data_grad(x.cpu(), dd.h1d, l, y.cpu(), dd.sigma2)  # the reference's conv2d formulation, on the host
+    want = (x.cpu() + (prm["delta"] / prm["lambd"]) * grad + float(np.sqrt(2) * prm["s"]) * z.cpu()).cuda()
     base = torch.empty_like(x)
     den_in = torch.empty((B, H, W, 16), device="cuda", dtype=torch.bfloat16)
     P._lib.check(lib.psgla_img_pre_deblur(pre, P._lib.ImgShape(B, 3, H, W), x.data_ptr(), dd._taps_c, l, y.data_ptr(), 1,
