@@ -10,6 +10,9 @@ Headline (BASELINE.json configs[1]): 2D Gaussian-mixture posterior sampling, the
 A "step" of this bench is ONE cell = 10^10 chain-steps per GPU, one launch of the persistent chain kernel;
 the K timed steps cycle through the cells.  Chains shard over GPUs with no per-step communication (weak scaling:
 10^6 chains per GPU, global chain ids keep every chain's Philox stream independent of the GPU count).
+The same line carries `strong` (the config AS WRITTEN: 10^6 chains per cell in total, sharded over the GPUs, all 18 cells),
+`config0_single_chain` (configs[0]: the one-chain SnoPnP_ULA(1000) call's latency), `image` / `image_deblur` / `image_drunet` /
+`image_set` (configs[2..4]) and, as its last key, `image_summary`.
 
 The same JSON line carries, under "image", the second half of BASELINE.json's metric: PSGLA image
 iterations/s at 256x256 with the DnCNN denoiser (configs[2]: random inpainting 50 %, sigma = 1/255, s = 2/255,
@@ -49,7 +52,12 @@ CELLS = [(p, y, a) for a in ("psgla", "pnp_ula") for p in PRIORS for y in OBSERV
 # algorithmic FP32 flop per chain-step (r = 2, FMA = 2 flop, constants folded on the host)
 FLOP_PER_CHAIN_STEP = {"psgla": 82, "pnp_ula": 88}
 MUFU_PER_CHAIN_STEP = 7
-FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.5; no measured FP32 figure in MEASURED_PEAKS.json
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.5; the denominator used is MEASURED here (measure_fp32_peak)
+# What the fp32, r = 2 loop of the shipped kernel issues per chain-step (SASS of gmm2d_lean_kernel, general-structure PSGLA):
+# 28 FP32 (FFMA / FMUL / FADD), 9 IMAD.WIDE.U32 + 10 LOP3 (Philox), 6 MUFU, 2 I2FP.  On the FMA pipe an FP32 instruction costs a
+# warp 1 cycle and an IMAD.WIDE.U32 4 (scripts/pipe_rates.py, profiles/r02_pipe_rates.txt), so the pipe needs 28 + 4 * 9 = 64 cycles
+# per warp-step (55 for cells whose constants are diagonal): the kernel's real bound.
+FMA_PIPE_CYCLES_PER_WARP_STEP = {0: 28 + 36, 1: 26 + 36, 2: 19 + 36}
 DNCNN_FLOP_PER_PIXEL = 2 * 9 * (3 * 64 + 18 * 64 * 64 + 64 * 3)  # 1 334 016
 CONV64_FLOP_PER_PIXEL = 2 * 9 * 64 * 64  # 73 728, one hidden layer
 DRUNET_FLOP_PER_PIXEL = 4235136  # head 4 608 + 3 x 16 x 73 728 + 8 x 73 728 + 6 x 16 384 (down / up) + tail 3 456
@@ -185,7 +193,124 @@ def barrier(torch, dist_mod):
     torch.cuda.synchronize()
 
 
+def measure_fp32_peak(P, torch, dev):
+    """Measured FP32 issue peak of this GPU (csrc/selftest.cu: nothing but dependent FFMA chains, 8 per thread), TFLOP/s.
+    Burst figure: best of 4 launches of ~25 ms, CUDA events."""
+    lib = P._lib.lib()
+    scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=dev)
+    best = {}
+    for mode, name in ((0, "ffma"), (1, "ffma2")):
+        flop = C.c_double()
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            P._lib.check(lib.psgla_selftest_fp32_rate(mode, 150000, 8, scratch.data_ptr(), C.byref(flop), P._lib.stream_ptr(dev)), "fp32_rate")
+            e1.record()
+            torch.cuda.synchronize()
+            best[name] = max(best.get(name, 0.0), flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def gmm_structure(P, prior):
+    """Which specialisation of the chain kernel a cell takes (csrc/gmm2d.cu constants_structure): 2 = all matrices diagonal
+    (isotropic / axis-aligned covariances), 1 = only the data term (A = I), 0 = general."""
+    import numpy as np
+    _, Sig, _ = P.gaussian_mixt_example(prior)
+    return 2 if all(abs(np.asarray(S)[0][1]) == 0 and abs(np.asarray(S)[1][0]) == 0 for S in Sig) else 1
+
+
 # ------------------------------------------------------------------------------------------------ 2D GMM (product)
+def bench_gmm2d_strong(args, P, torch, rank, ws, dev):
+    """BASELINE.json configs[1] AS WRITTEN: 10^6 chains in total per cell, sharded over the GPUs (contiguous blocks of global
+    chain ids, dist.shard_range), all 18 cells once.  Cells are independent sampling problems, so a rank keeps up to
+    --strong-streams cells in flight on separate CUDA streams: with 125 000 chains per GPU one cell fills 0.8 of a wave and
+    the second cell's blocks take the slots the first leaves free."""
+    import numpy as np
+    total = args.strong_chains
+    world = args.emulate_world if (ws == 1 and args.emulate_world > 1) else ws
+    me = 0 if world != ws else rank
+    lo, hi = P.dist.shard_range(total, me, world)
+    n_local = hi - lo
+    pops = []
+    for prior, y, alg in CELLS:
+        mu, Sig, pi = P.gaussian_mixt_example(prior)
+        prm = GMM_ALGS[alg]
+        x0 = torch.tensor(y, dtype=torch.float32, device=dev).repeat(n_local, 1).contiguous()
+        pops.append((P.GMMChains(alg, np.array(y), prm["delta"], np.eye(2), 1.0, P.Theorical_MMSE(mu, Sig, pi), prm["alpha"],
+                                 prm["epsilon"], n_chains=n_local, x0=x0, seed=args.seed, chain_id0=lo, dtype="float32",
+                                 device=dev), x0))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.strong_streams))]
+
+    def all_cells():
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+        for i, (ch, x0) in enumerate(pops):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                ch.state.copy_(x0)
+                ch.step = 0
+                ch.run(args.chain_steps)
+        for st in streams:
+            cur.wait_stream(st)
+
+    all_cells()  # warm-up pass (all 18 cells)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()
+    barrier(torch, P.dist)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    all_cells()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier(torch, P.dist)
+    ms = P.dist.max_over_ranks(ms, dev)
+    units = float(total) * args.chain_steps * len(CELLS)
+    out = {"scaling": "strong", "value": units / (ms * 1e-3), "unit": "chain-steps/s",
+           "total_chains_per_cell": total, "chains_per_gpu": n_local, "cells": len(CELLS), "ms_all_cells": ms,
+           "streams": len(streams), "n_gpus": ws,
+           "note": "10^6 chains per cell in total, sharded over the GPUs; value = 18 x 10^6 x 10^4 chain-steps / max-over-ranks device time"}
+    if world != ws:
+        out["emulated_world"] = world
+        out["note"] = ("rank 0's shard of an emulated %d-GPU split on one GPU: value = this GPU's chain-steps/s at %d chains per cell"
+                       % (world, n_local))
+        out["value"] = float(n_local) * args.chain_steps * len(CELLS) / (ms * 1e-3)
+    return out
+
+
+def bench_gmm2d_config0(args, P, torch, dev):
+    """BASELINE.json configs[0]: `sampling_2D.py --N 1000 --name symetric_gaussians` -- ONE chain, 999 steps, through the drop-in
+    SnoPnP_ULA exactly as the script calls it (float64, the global NumPy stream replayed).  Latency, not throughput: one thread
+    of one warp walks 999 dependent steps."""
+    import numpy as np
+    mu, Sig, pi = P.gaussian_mixt_example("symetric_gaussians")
+    D = P.Theorical_MMSE(mu, Sig, pi)
+    y = np.array([0.0, -2.0])
+    times = []
+    for rep in range(6):
+        np.random.seed(rep)
+        t0 = time.perf_counter()
+        X = P.SnoPnP_ULA(1000, y, y, 0.3, np.eye(2), 1, D, 2.0 / 3.0)
+        dt = time.perf_counter() - t0
+        if rep:
+            times.append(dt)
+    assert X.shape == (1000, 2)
+    # the kernel alone (device time of the 999-step launch, replay mode, fp64)
+    ch = P.GMMChains("psgla", y, 0.3, np.eye(2), 1.0, D, 2.0 / 3.0, n_chains=1, dtype="float64", device=dev)
+    z = torch.randn(999, 1, 2, dtype=torch.float64, device=dev)
+    ch.run(999, noise=z)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ch.run(999, noise=z)
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(times)
+    return {"workload": "SnoPnP_ULA(1000, x0 = y = (0,-2), delta 0.3, alpha 2/3, symetric_gaussians), one chain, float64, NumPy stream replayed",
+            "call_ms": best * 1e3, "us_per_step": best * 1e6 / 999, "steps_per_s": 999 / best,
+            "kernel_ms": e0.elapsed_time(e1), "kernel_us_per_step": e0.elapsed_time(e1) * 1e3 / 999,
+            "reference_us_per_step_here": None}
+
+
 def bench_gmm2d(args, P, torch, rank, ws, dev):
     import numpy as np
     n_chains, n_steps = args.chains, args.chain_steps
@@ -261,7 +386,8 @@ def bench_gmm2d(args, P, torch, rank, ws, dev):
             sub = finals[torch.randperm(finals.shape[0], device=finals.device)[:10000]].double().cpu().numpy()
             w2["%s|%s|y=(%g,%g)" % (alg, prior, y[0], y[1])] = round(P.Wasserstein_distance(sub, ref, rng=rng), 4)
     units = float(n_chains) * n_steps * K * ws
-    return dict(value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
+    pipe_cycles = sum(FMA_PIPE_CYCLES_PER_WARP_STEP[gmm_structure(P, CELLS[k % len(CELLS)][0])] for k in range(W, W + K)) / K
+    return dict(pipe_cycles=pipe_cycles, value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
                 e2e_value=units / (e2e_ms * 1e-3), e2e_ms=e2e_ms, h2d=n_chains * 2 * 4, d2h=n_chains * 2 * 4, w2=w2,
                 launches_per_step=launches_per_step)
 
@@ -342,6 +468,30 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
     pre_ms, _ = timer.total_ms()
     pre_launch_ms = pre_ms / reps
 
+    # ---- the last layer alone: 64 -> 3 conv + Langevin post (X+, thinning every 10th, moments) + the next iteration's pre
+    nxt_params = _lib.PreParams()
+    C.memmove(C.byref(nxt_params), C.byref(run.pre_params), C.sizeof(_lib.PreParams))
+    run._stamp(nxt_params, W + K)
+    nxt = _lib.NextPre(C.pointer(nxt_params), _lib.ptr(run.mask), _lib.ptr(run.y), int(run.mask.shape[0]), int(run.y.shape[0]),
+                       _lib.ptr(run.base), _lib.ptr(run.den_in))
+    post = _lib.PostParams(1.0, 1.0, 0.5, 0.5)
+    x_scratch = torch.empty_like(run.X)
+
+    def last_only():
+        rc = lib.psgla_dncnn_last_layer_post_next(den.depth, den.packed.data_ptr(), shape, bufs[0], _lib.ptr(run.base), C.byref(post),
+                                                  _lib.ptr(x_scratch), None, _lib.ptr(run.mean), _lib.ptr(run.mean2), C.byref(nxt), st)
+        if rc:
+            _lib.check(rc, "psgla_dncnn_last_layer_post_next")
+
+    last_only()
+    for _ in range(reps):
+        timer.step(last_only)
+    last_ms, _ = timer.total_ms()
+    last_launch_ms = last_ms / reps
+    # algorithmic bytes per pixel: 128 (bf16 hidden in) + fp32 x 3 channels x (base in, X out, E[X] in/out, E[X^2] in/out, mask, y,
+    # next base out) = 9 x 12 + 32 (bf16 NHWC16 next denoiser input) = 268; thinned sample (+12 every n_inter-th iteration) not counted
+    last_bytes_px = 128 + 9 * 12 + 32
+
     # ---- e2e: psgla() itself, pinned-host image / mask / observation in, pinned-host posterior mean out
     n_e2e = max(K, 100)  # one psgla() call of 100 iterations (the reference runs 10^4 per image); set-up amortised as in use
     host = dict(init=init.cpu().pin_memory(), mask=mask.cpu().pin_memory(), y=y.cpu().pin_memory())
@@ -395,7 +545,15 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
                        # the kernel also writes the padded bf16 NHWC16 denoiser input (32 B per pixel), which the algorithmic
                        # 16 B per pixel-channel above does not count
                        "moved_gbs_incl_den_in": (16 * 3 + 32) * px / (pre_launch_ms * 1e-3) / 1e9},
+        "last_layer_kernel": {"kernel": "conv3x3_ts_kernel<16,POST> (64 -> 3 conv + fused Langevin post + next-iteration pre)",
+                              "bound": "hbm", "achieved": last_bytes_px * px / (last_launch_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": last_bytes_px * px / (last_launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                              "launch_ms": last_launch_ms, "algorithmic_bytes_per_pixel": last_bytes_px},
         "single_chain_iterations_per_sec": single_chain_its,
+        "single_chain": {"iterations_per_sec": single_chain_its, "us_per_iteration": 1e6 / single_chain_its,
+                         "tensor_tflops": DNCNN_FLOP_PER_PIXEL * H * Wd * single_chain_its / 1e12,
+                         "frac_of_burst_peak": DNCNN_FLOP_PER_PIXEL * H * Wd * single_chain_its / 1e12 / peaks["bf16_tflops"],
+                         "note": "the reference's own run shape (configs[2]: one chain of one 256 x 256 image), 20 launches per iteration"},
         "state_finite": finite, "state_absmax": x_absmax,
         "per_step_ms": [round(v, 3) for v in per_step],
     }
@@ -522,6 +680,79 @@ def bench_image_drunet(args, P, torch, rank, ws, dev, peaks):
                                              "source": "profiles/r01f_conv_gemm2_full.txt"}},
         "state_finite": finite, "per_step_ms": [round(v, 3) for v in per_step],
     }
+
+
+def gpu_reference_image(args, torch, dev):
+    """The fair GPU comparator: the reference's OWN PyTorch loop run unchanged on the same B200 --
+    restoration_algorithms.psgla (the unmodified reference when it is loadable, else the oracle's restatement) on device cuda,
+    eager ops + cuDNN convolutions of the torch DnCNN (torch's default flags: TF32 convolutions allowed), same problem, same
+    weights.  B = 1 is the reference's run shape; B = --image-chains is the same code on a batch (its ops broadcast)."""
+    import psgla_b200 as P
+    from oracle import image_oracle as io_
+    H = args.image_size
+    im = synthetic_image(torch, H, H, 0, dev)
+    net = io_.DnCNN().to(dev)
+    net.load_state_dict(P.lipschitz_dncnn_state_dict(0))
+    net.eval()
+    prob = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0, device=dev)
+    s = 2.0 / 255.0
+    kw = dict(alpha=torch.tensor(1.0, device=dev), lambd=torch.tensor(5.0, device=dev), sig_float=s, delta=s * s, n_inter=10,
+              n_inter_mmse=10, seed=0)
+    kind = "port"
+    fn = lambda *a, **k: io_.psgla(*a, device=dev, **k)  # noqa: E731
+    if _reference_available():
+        from oracle import ref_loader
+        ra = ref_loader.load_restoration_algorithms()
+        fn, kind = (lambda *a, **k: ra.psgla(*a, device=dev, **k)), "reference"
+    out = {"kind": kind, "flags": "torch defaults (cudnn.allow_tf32 = %s), eager, fp32 tensors" % torch.backends.cudnn.allow_tf32}
+    for B, n_iter in ((1, 60), (args.image_chains, 20)):
+        init = prob["init"].expand(B, -1, -1, -1).contiguous()
+        with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")), torch.no_grad():
+            fn(init, prob["data_grad"], net, n_iter=10, **kw)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(init, prob["data_grad"], net, n_iter=n_iter, **kw)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out["B%d" % B] = {"value": B * n_iter / dt, "unit": "image-iterations/s", "ms_per_iteration": dt / n_iter * 1e3,
+                          "iterations": n_iter}
+    return out
+
+
+def bench_image_set(args, P, torch, rank, ws, dev):
+    """BASELINE.json configs[4] as a whole job: a SET of CBSD-sized images (320 x 480), --set-chains chains per image, images dealt
+    round-robin over the GPUs (psgla_b200.run_image_set), PSGLA with the DRUNet-architecture denoiser in statistics-only mode,
+    per-image PSNR / SSIM / std reduced on the device and gathered on rank 0 -- the only communication of the job."""
+    n_img, B, n_iter = args.set_images, args.set_chains, args.set_iters
+    images = [synthetic_image(torch, args.drunet_h, args.drunet_w, 100 + i, "cpu")[0] for i in range(n_img)]
+    den = P.DRUNet(pretrained=P.random_drunet_state_dict(0), device=dev)
+    s = 5.0 / 255.0
+    prm = dict(P.sampler_params("psgla", den="DRUNet", lambd=25.0, N=max(n_iter, 1000)), N=n_iter, n_inter=10, n_inter_mmse=10)
+
+    def job():
+        with contextlib.redirect_stdout(sys.stderr):
+            return P.run_image_set(images, den, problem="inpainting", alg="psgla", n_chains=B, params=prm, seed=args.seed)
+
+    small = dict(prm, N=11)
+    with contextlib.redirect_stdout(sys.stderr):
+        P.run_image_set(images[:ws], den, problem="inpainting", alg="psgla", n_chains=B, params=small, seed=args.seed)  # warm-up
+    barrier(torch, P.dist)
+    t0 = time.perf_counter()
+    res = job()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier(torch, P.dist)
+    dt = P.dist.max_over_ranks(dt, dev)
+    out = {"metric": "psgla_image_iterations_per_sec_drunet_image_set", "unit": "image-iterations/s",
+           "value": n_img * B * n_iter / dt, "seconds": dt, "images": n_img, "chains_per_image": B, "iterations": n_iter,
+           "config": {"workload": "%d synthetic %dx%d images x %d chains x %d PSGLA iterations, DRUNet, statistics-only mode, images "
+                                  "round-robin over %d GPU(s), per-image metrics gathered on rank 0; wall clock incl. problem set-up"
+                                  % (n_img, args.drunet_h, args.drunet_w, B, n_iter, ws)},
+           "s": s}
+    if rank == 0 and res:
+        out["per_image"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in d.items()
+                             if k in ("index", "psnr_mmse", "ssim_mmse", "psnr_chain_mean", "psnr_observation", "std_mean")} for d in res]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle)
@@ -692,7 +923,8 @@ def config_block(args):
                         % (args.chains, args.chain_steps),
             "chains_per_gpu": args.chains, "steps_per_chain": args.chain_steps, "cells": len(CELLS),
             "rng": "in-kernel Philox4x32-10 + Box-Muller, subsequence = global chain id",
-            "sharding": "chains split over GPUs, no per-step communication; NCCL gather of finals for W2",
+            "sharding": "chains split over GPUs, no per-step communication; NCCL gather of finals for W2; the `strong` block of the "
+                        "line runs the same 18 cells with 10^6 chains per cell IN TOTAL, sharded",
             "l2": "256 MiB flush between timed steps (state lives in registers; HBM sees 16 B per chain per step of the bench)"}
 
 
@@ -713,6 +945,15 @@ def main():
     ap.add_argument("--drunet-w", type=int, default=480)
     ap.add_argument("--drunet-steps", type=int, default=6)
     ap.add_argument("--skip-drunet", action="store_true")
+    ap.add_argument("--strong-chains", type=int, default=1000000, help="2D chains per cell IN TOTAL for the strong-scaling block")
+    ap.add_argument("--strong-streams", type=int, default=3, help="cells a rank keeps in flight in the strong-scaling block")
+    ap.add_argument("--emulate-world", type=int, default=0, help="1 GPU only: time rank 0's shard of an N-way strong split")
+    ap.add_argument("--skip-strong", action="store_true")
+    ap.add_argument("--set-images", type=int, default=8, help="image-set block: number of 320x480 images")
+    ap.add_argument("--set-chains", type=int, default=64)
+    ap.add_argument("--set-iters", type=int, default=24)
+    ap.add_argument("--skip-set", action="store_true")
+    ap.add_argument("--skip-gpu-reference", action="store_true")
     ap.add_argument("--ref-chain-steps", type=int, default=20000, help="--impl reference: steps per core per bench step")
     ap.add_argument("--cpu-sample-steps", type=int, default=100000, help="cpu_baseline sample: steps of one CPU chain")
     ap.add_argument("--skip-image", action="store_true")
@@ -723,7 +964,7 @@ def main():
     args.warmup = max(args.warmup, 0)
     capture_stdout()
     if args.only_image:
-        args.chains, args.chain_steps, args.steps, args.skip_cpu = 4096, 16, 1, True
+        args.chains, args.chain_steps, args.steps, args.skip_cpu, args.skip_strong = 4096, 16, 1, True, True
 
     if args.impl == "reference":
         run_reference(args)
@@ -747,17 +988,26 @@ def main():
         log("warm-up raised to 3 steps (timing rule)")
         args.warmup = W
 
-    sampler = ClockSampler(local)
+    fp32_peak = measure_fp32_peak(P, torch, dev)
+    sampler = ClockSampler(local)  # clocks during the headline (2D) timed regions ...
     if rank == 0:
         sampler.start()
     g = bench_gmm2d(args, P, torch, rank, ws, dev)
-    img = dru = deb = None
+    strong = None if args.skip_strong else bench_gmm2d_strong(args, P, torch, rank, ws, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    cfg0 = bench_gmm2d_config0(args, P, torch, dev) if (rank == 0 and not args.only_image) else None
+    sampler = ClockSampler(local)  # ... and during the image blocks (tensor-core work under the power cap: lower clocks)
+    if rank == 0:
+        sampler.start()
+    img = dru = deb = iset = None
     if not args.skip_image:
         img = bench_image(args, P, torch, rank, ws, dev, peaks)
         deb = bench_image_deblur(args, P, torch, rank, ws, dev, peaks)
         if not args.skip_drunet:
             dru = bench_image_drunet(args, P, torch, rank, ws, dev, peaks)
-    clocks = sampler.stop() if rank == 0 else None
+            if not args.skip_set:
+                iset = bench_image_set(args, P, torch, rank, ws, dev)
+    clocks_image = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if ws > 1:
@@ -770,30 +1020,45 @@ def main():
         "metric": "langevin_chain_steps_per_sec_2d_gmm", "value": g["value"], "unit": "chain-steps/s", "n_gpus": ws,
         "steps": K, "warmup": args.warmup, "ms_per_step": g["total_ms"] / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args),
-        "clocks": clocks,
+        "clocks": clocks, "clocks_image_blocks": clocks_image,
         "e2e": {"value": g["e2e_value"], "unit": "chain-steps/s", "h2d_bytes_per_step": g["h2d"],
                 "d2h_bytes_per_step": g["d2h"]},
         "gpu_launches": K * g["launches_per_step"],
-        "roofline": {"kernel": "gmm2d_kernel<float,*,true,{4,3}> (%d occupancy-sized waves per step)" % g["launches_per_step"],
+        "roofline": {"kernel": "gmm2d_lean_kernel<ALG,STRUCT,4,64,16,true> (one chain per thread, 4 Philox blocks = 8 steps per round; "
+                               "%d launch(es) per step)" % g["launches_per_step"],
                      "bound": "fp32",
-                     "achieved": achieved_tflops / ws, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / ws / FP32_PEAK_TFLOPS_NOMINAL,
-                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure); "
-                                    "algorithmic 82/88 flop + 7 MUFU per chain-step, Philox INT work not counted",
+                     "achieved": achieved_tflops / ws, "peak": fp32_peak["ffma"], "unit": "TFLOP/s",
+                     "frac": achieved_tflops / ws / fp32_peak["ffma"],
+                     "peak_source": "measured on this GPU in this run: FFMA-only probe (psgla_selftest_fp32_rate), burst; FFMA2 probe %.1f, "
+                                    "nominal %.1f.  Algorithmic 82/88 flop + 7 MUFU per chain-step (SURVEY 8d), Philox INT work not counted"
+                                    % (fp32_peak["ffma2"], FP32_PEAK_TFLOPS_NOMINAL),
+                     "frac_of_nominal_peak": achieved_tflops / ws / FP32_PEAK_TFLOPS_NOMINAL,
                      "mufu_gops": g["value"] / ws * MUFU_PER_CHAIN_STEP / 1e9,
+                     # the bound that actually binds: FMA-pipe cycles the issued mix needs (FP32 1 cycle, IMAD.WIDE.U32 4 cycles per
+                     # warp instruction, measured by scripts/pipe_rates.py) over the SM-cycles the step took at the sampled clock
+                     "fma_pipe": {"cycles_needed_per_warp_step": g["pipe_cycles"],
+                                  "cycles_taken_per_warp_step": (clocks or {}).get("sm_mhz") and
+                                  (clocks["sm_mhz"] * 1e6 * 148 * 4 * 32) / (g["value"] / ws),
+                                  "note": "taken = sm_clock x 592 SM sub-partitions x 32 lanes / (chain-steps/s); needed / taken = FMA-pipe utilisation"},
                      "launch_ms": g["total_ms"] / K / g["launches_per_step"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01e_gmm2d_full.txt:
-                     # 4.87 MB and 3.17 MB for the two waves of 10^6 chains; the 8 B per chain written back stay in L2)
-                     "traffic": 4.02e6 if (args.chains == 1000000 and g["launches_per_step"] == 2) else None,
-                     "traffic_source": "profiles/r01e_gmm2d_full.txt (mean of the two waves)"},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_gmm2d_lean_full.txt)
+                     "traffic": None,
+                     "traffic_source": "profiles/r02_gmm2d_lean_full.txt"},
         "w2_squared_to_true_posterior": g["w2"],
     }
+    if strong is not None:
+        strong["value_over_weak_value"] = strong["value"] / g["value"] if not strong.get("emulated_world") else None
+        line["strong"] = strong
+    if cfg0 is not None:
+        line["config0_single_chain"] = cfg0
     if img is not None:
         line["image"] = img
     if deb is not None:
         line["image_deblur"] = deb
     if dru is not None:
         line["image_drunet"] = dru
+    if iset is not None:
+        line["image_set"] = iset
     if ws == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_baseline_gmm2d(args.cpu_sample_steps)
         if img is not None:
@@ -806,6 +1071,31 @@ def main():
                 dru["cpu_baseline"] = cpu_baseline_drunet(args)
             except Exception as exc:  # noqa: BLE001
                 dru["cpu_baseline"] = {"error": repr(exc)[:200]}
+        if cfg0 is not None and "value" in line["cpu_baseline"]:
+            cfg0["reference_us_per_step_here"] = 1e6 / line["cpu_baseline"]["value"]
+        if img is not None and not args.skip_gpu_reference:
+            try:
+                img["gpu_reference"] = gpu_reference_image(args, torch, dev)
+            except Exception as exc:  # noqa: BLE001
+                img["gpu_reference"] = {"error": repr(exc)[:200]}
+    # the image half of BASELINE.json's metric, compact, as the LAST key of the line (the nested blocks above hold the detail)
+    if img is not None:
+        summ = {"dncnn_psgla_image_iterations_per_sec": img["value"], "dncnn_psgla_e2e": img["e2e"]["value"],
+                "dncnn_chains_per_gpu": args.image_chains, "dncnn_hidden_conv_frac_of_sustained_bf16_peak": img["roofline"]["frac"],
+                "dncnn_whole_iteration_frac_of_sustained_bf16_peak": img["whole_iteration_frac"],
+                "dncnn_single_chain_iterations_per_sec": img["single_chain_iterations_per_sec"], "n_gpus": ws}
+        if deb is not None:
+            summ["dncnn_pnpula_deblur_image_iterations_per_sec"] = deb["value"]
+        if dru is not None:
+            summ["drunet_psgla_image_iterations_per_sec"] = dru["value"]
+            summ["drunet_whole_iteration_frac_of_sustained_bf16_peak"] = dru["roofline"]["frac"]
+        if iset is not None:
+            summ["drunet_image_set_image_iterations_per_sec"] = iset["value"]
+        if "cpu_baseline" in img and "value" in img["cpu_baseline"]:
+            summ["cpu_reference_image_iterations_per_sec"] = img["cpu_baseline"]["value"]
+        if "gpu_reference" in img and "B1" in img["gpu_reference"]:
+            summ["gpu_reference_B1_image_iterations_per_sec"] = img["gpu_reference"]["B1"]["value"]
+        line["image_summary"] = summ
     emit(line)
     if ws > 1:
         import torch.distributed as dist

@@ -234,6 +234,14 @@ int psgla_dncnn_residual_post_next(int depth, const void* packed_dev, psgla_img_
                                    const psgla_post_params* post, float* x_out_dev, float* sample_dev, float* mean_dev,
                                    float* mean2_dev, const psgla_next_pre* next, void* stream);
 
+/* The last layer of that chain alone (64 -> 3 channels + the fused post / next pre): hidden_dev = bf16 NHWC [B][H][W][64], the
+ * output of layer depth - 2.  What psgla_dncnn_residual_post_next launches last; exposed so that the fused epilogue can be
+ * timed (bench.py's HBM roofline of this stage) and tested on its own. */
+int psgla_dncnn_last_layer_post_next(int depth, const void* packed_dev, psgla_img_shape shape, const void* hidden_dev,
+                                     const float* base_dev, const psgla_post_params* post, float* x_out_dev,
+                                     float* sample_dev, float* mean_dev, float* mean2_dev, const psgla_next_pre* next,
+                                     void* stream);
+
 /* Single conv3x3 layers, exposed for parity tests against torch.nn.functional.conv2d.
  *   cin_pad: 16 (first layer, channels 3..15 zero) or 64.   in_dev: bf16 NHWC [B][H][W][cin_pad].
  *   out_dev: bf16 NHWC [B][H][W][64], ReLU applied if relu != 0.   layer: index into the packed weights. */

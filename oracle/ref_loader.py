@@ -1,10 +1,16 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference implementation.
 
-Only usable inside the build container, where ``/root/reference`` exists; the
-GPU box has no reference tree, so nothing under ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` may import this module.  It is used by ``tests/golden/make_golden.py``
-to generate the committed golden vectors and by the ``not gpu`` tests that pin
-``oracle/gmm2d_oracle.py`` / ``oracle/image_oracle.py`` against the real thing.
+Two sources, in this order:
+  * ``/root/reference`` (the build container): the files are read from where they lie;
+  * ``oracle/_ref/*.pyc`` (the GPU box, where ``/root/reference`` does not exist): the
+    reference's own modules COMPILED to CPython bytecode by ``build_ref()`` below, which
+    ``__graft_entry__.build()`` calls while the reference tree is present.  ``oracle/_ref/``
+    is git-ignored build output (like a compiled C reference's ``.so``) and travels to the
+    GPU box with the snapshot; no reference source text enters the repository.
+It is used by ``tests/golden/make_golden.py`` to generate the committed golden vectors, by
+the ``not gpu`` tests that pin ``oracle/gmm2d_oracle.py`` / ``oracle/image_oracle.py``
+against the real thing, and by ``bench.py``'s CPU legs (``cpu_baseline.kind ==
+"reference"``).  The product never imports it.
 
 How the reference is loaded:
   * ``restoration_algorithms.py`` imports unchanged once ``matplotlib``,
@@ -21,16 +27,63 @@ No reference source is copied: the files are read from where they lie.
 from __future__ import annotations
 
 import ast
+import importlib.machinery
 import importlib.util
 import os
 import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("PSGLA_REFERENCE_ROOT", "/root/reference")
+REF_BUILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_COMPILED = ("utils_2D", "restoration_algorithms", "sampling_2D_functions")
+
+
+def _source_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "sampling_2D.py"))
+
+
+def _compiled_available() -> bool:
+    return all(os.path.isfile(os.path.join(REF_BUILD, m + ".pyc")) for m in _COMPILED)
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "sampling_2D.py"))
+    return _source_available() or _compiled_available()
+
+
+def reference_kind() -> str:
+    """"source" (read from /root/reference), "compiled" (oracle/_ref/*.pyc) or "" (absent)."""
+    return "source" if _source_available() else ("compiled" if _compiled_available() else "")
+
+
+def _sampling_2D_functions_ast():
+    path = os.path.join(REFERENCE_ROOT, "sampling_2D.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("PnP_ULA", "SnoPnP_ULA")]
+    assert len(keep) == 2, "reference sampling_2D.py no longer defines PnP_ULA / SnoPnP_ULA"
+    return path, ast.Module(body=keep, type_ignores=[])
+
+
+def build_ref() -> list:
+    """Compiles the reference's modules, from the sources where they lie under /root/reference, into oracle/_ref/*.pyc
+    (outputs only; nothing is copied).  No-op without the reference tree.  Returns the files written."""
+    if not _source_available():
+        return []
+    import importlib._bootstrap_external as be
+    import py_compile
+    os.makedirs(REF_BUILD, exist_ok=True)
+    out = []
+    for mod in ("utils_2D", "restoration_algorithms"):
+        out.append(py_compile.compile(os.path.join(REFERENCE_ROOT, mod + ".py"), cfile=os.path.join(REF_BUILD, mod + ".pyc"),
+                                      doraise=True, quiet=2))
+    path, tree = _sampling_2D_functions_ast()  # sampling_2D.py runs its experiment at import: only its two samplers
+    st = os.stat(path)
+    data = be._code_to_timestamp_pyc(compile(tree, path, "exec"), int(st.st_mtime), st.st_size)
+    target = os.path.join(REF_BUILD, "sampling_2D_functions.pyc")
+    with open(target, "wb") as fh:
+        fh.write(data)
+    out.append(target)
+    return out
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -72,7 +125,11 @@ def _install_stubs() -> None:
 
 def _load_file(modname: str, filename: str) -> types.ModuleType:
     path = os.path.join(REFERENCE_ROOT, filename)
-    spec = importlib.util.spec_from_file_location(modname, path)
+    if os.path.isfile(path):
+        spec = importlib.util.spec_from_file_location(modname, path)
+    else:  # the GPU box: the module as compiled by build_ref()
+        cfile = os.path.join(REF_BUILD, filename[:-3] + ".pyc")
+        spec = importlib.util.spec_from_loader(modname, importlib.machinery.SourcelessFileLoader(modname, cfile))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -97,14 +154,15 @@ def load_sampling_2D() -> types.SimpleNamespace:
     """
     if "sampling_2D" not in _CACHE:
         u2d = load_utils_2D()
-        path = os.path.join(REFERENCE_ROOT, "sampling_2D.py")
-        with open(path, "r") as fh:
-            tree = ast.parse(fh.read(), filename=path)
-        keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("PnP_ULA", "SnoPnP_ULA")]
-        assert len(keep) == 2, "reference sampling_2D.py no longer defines PnP_ULA / SnoPnP_ULA"
         ns = dict(u2d.__dict__)
         ns["tqdm"] = lambda it, *a, **k: it
-        exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+        if _source_available():
+            path, tree = _sampling_2D_functions_ast()
+            exec(compile(tree, path, "exec"), ns)
+        else:
+            import marshal
+            with open(os.path.join(REF_BUILD, "sampling_2D_functions.pyc"), "rb") as fh:
+                exec(marshal.loads(fh.read()[16:]), ns)
         _CACHE["sampling_2D"] = types.SimpleNamespace(PnP_ULA=ns["PnP_ULA"], SnoPnP_ULA=ns["SnoPnP_ULA"], namespace=ns)
     return _CACHE["sampling_2D"]
 

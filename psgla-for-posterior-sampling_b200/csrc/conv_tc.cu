@@ -1696,6 +1696,27 @@ static ConvParams base_params(const psgla_img_shape& s, const uint8_t* packed, c
   return p;
 }
 
+// The last layer (64 -> 3) with the Langevin post (and optionally the next iteration's pre) in its epilogue.
+static int last_layer_post(int depth, const uint8_t* packed, const psgla_img_shape& shape, const void* hidden, const float* base_dev,
+                           const psgla_post_params* post, float* x_out_dev, float* sample_dev, float* mean_dev,
+                           float* mean2_dev, const psgla_next_pre* next, cudaStream_t st) {
+  const LayerInfo li = layer_info(depth, depth - 1);
+  ConvParams p = base_params(shape, packed, li);
+  p.base = base_dev;
+  p.x_out = x_out_dev;
+  p.sample = sample_dev;
+  p.mean = mean_dev;
+  p.mean2 = mean2_dev;
+  p.gain = post->gain;
+  p.base_scale = 1.0f;  // DnCNN is a residual denoiser: X+ = base + gain * R
+  p.w_old = post->w_old;
+  p.w_new = post->w_new;
+  p.reverse = alternate_items() ? ((depth - 1) & 1) : 0;
+  int rc = set_next_pre(&p, next);
+  if (rc) return rc;
+  return launch_last(hidden, p, st);
+}
+
 extern "C" int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer, psgla_img_shape shape,
                                    const void* in_dev, void* out_dev, int relu, void* stream) {
   PSGLA_REQUIRE(packed_dev && in_dev && out_dev && depth >= 2 && layer >= 0 && layer < depth,
@@ -1767,23 +1788,23 @@ extern "C" int psgla_dncnn_residual_post_next(int depth, const void* packed_dev,
       }
     }
   }
-  const LayerInfo li = layer_info(depth, depth - 1);
-  ConvParams p = base_params(shape, packed, li);
-  p.base = base_dev;
-  p.x_out = x_out_dev;
-  p.sample = sample_dev;
-  p.mean = mean_dev;
-  p.mean2 = mean2_dev;
-  p.gain = post->gain;
-  p.base_scale = 1.0f;  // DnCNN is a residual denoiser: X+ = base + gain * R
-  p.w_old = post->w_old;
-  p.w_new = post->w_new;
-  p.reverse = alternate_items() ? ((depth - 1) & 1) : 0;
-  rc = set_next_pre(&p, next);
-  if (rc) return rc;
-  return launch_last(cur, p, st);
+  return last_layer_post(depth, packed, shape, cur, base_dev, post, x_out_dev, sample_dev, mean_dev, mean2_dev, next, st);
 }
 
+extern "C" int psgla_dncnn_last_layer_post_next(int depth, const void* packed_dev, psgla_img_shape shape,
+                                                const void* hidden_dev, const float* base_dev,
+                                                const psgla_post_params* post, float* x_out_dev, float* sample_dev,
+                                                float* mean_dev, float* mean2_dev, const psgla_next_pre* next, void* stream) {
+  PSGLA_REQUIRE(packed_dev && hidden_dev && base_dev && post && x_out_dev && depth >= 2,
+                "psgla_dncnn_last_layer_post_next: bad argument");
+  PSGLA_REQUIRE((mean_dev == nullptr) == (mean2_dev == nullptr), "mean and mean2 must be given together");
+  int rc = check_next_pre(next, shape);
+  if (rc) return rc;
+  rc = check_shape(shape);
+  if (rc) return rc;
+  return last_layer_post(depth, (const uint8_t*)packed_dev, shape, hidden_dev, base_dev, post, x_out_dev, sample_dev, mean_dev,
+                         mean2_dev, next, (cudaStream_t)stream);
+}
 
 // ------------------------------------------------------------------------------------------------ internal API (drunet.cu)
 namespace psgla {

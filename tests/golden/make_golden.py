@@ -128,7 +128,54 @@ def images():
     print("images: psgla", out["psgla.X"].shape, out["psgla.M"].shape, "ula", out["ula.X"].shape, out["ula.M"].shape)
 
 
+def images_depth20():
+    """The same two reference samplers with the FULL denoiser architecture the CUDA path is built for (DnCNN depth 20, 64
+    features), so that the reference's outputs can be compared with the kernels directly (tests/test_image_gpu.py::
+    test_reference_fixture_replayed_through_cuda).  The weights are not stored: the tests regenerate them from the seed with
+    oracle.image_oracle.make_dncnn_weights(seed=0, n_power_iter=10, spatial=16), exactly as here."""
+    ra = ref_loader.load_restoration_algorithms()
+    sd = io_.make_dncnn_weights(seed=0, n_power_iter=10, spatial=16)
+    den = io_.DnCNN()
+    den.load_state_dict(sd)
+    den.eval()
+    torch.manual_seed(5)
+    H = W = 16
+    im = torch.rand(1, 3, H, W)
+    out = {"im": im.numpy(), "weights": np.array([0, 10, 16])}  # seed, n_power_iter, spatial
+    n_iter, n_inter, n_mm = 12, 2, 3
+
+    inp = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("psgla")
+    Xl, Xm, Xm2 = ra.psgla(init=inp["init"], data_grad=inp["data_grad"], denoiser=den, alpha=torch.tensor(1.0),
+                           lambd=torch.tensor(prm["lambd"]), sig_float=prm["s"], delta=prm["delta"], seed=7, device="cpu",
+                           n_iter=n_iter, n_inter=n_inter, n_inter_mmse=n_mm)
+    gen = torch.Generator().manual_seed(7)
+    noise = torch.stack([torch.randn(im.shape, generator=gen) for _ in range(n_iter)])
+    out.update({"inp.mask": inp["mask"].numpy(), "inp.y": inp["y"].numpy(), "inp.init": inp["init"].numpy(),
+                "psgla.noise": noise.numpy(), "psgla.X": torch.stack(Xl).numpy(), "psgla.M": torch.stack(Xm).numpy(),
+                "psgla.M2": torch.stack(Xm2).numpy(),
+                "psgla.params": np.array([1.0, prm["lambd"], prm["s"], prm["delta"], n_iter, n_inter, n_mm])})
+
+    # PnP-ULA with the script's DEFAULT table (sampling_images.py:147-168: s = 2/255 divided by 255 once more, delta ~ 1e-10)
+    deb = io_.make_deblurring(im, l=2, blur_type="gaussian", si=1.0, sigma=1.0, seed_ip=0)
+    pu = io_.resolve_params("pnp_ula")
+    pg = io_.make_prior_grad(den, pu["alpha"], pu["s1"], pu["s2"])
+    Xl, Xm, Xm2 = ra.pnpula(init=deb["init"], data_grad=deb["data_grad"], prior_grad=pg,
+                            delta=torch.tensor(pu["delta"], dtype=torch.float32), lambd=torch.tensor(pu["lambd"], dtype=torch.float32),
+                            seed=11, device="cpu", n_iter=n_iter, n_inter=n_inter, n_inter_mmse=n_mm)
+    gen = torch.Generator().manual_seed(11)
+    noise = torch.stack([torch.randn(im.shape, generator=gen) for _ in range(n_iter)])
+    out.update({"deb.y": deb["y"].numpy(), "deb.h": deb["h"], "ula.noise": noise.numpy(), "ula.X": torch.stack(Xl).numpy(),
+                "ula.M": torch.stack(Xm).numpy(), "ula.M2": torch.stack(Xm2).numpy(),
+                "ula.params": np.array([pu["delta"], pu["lambd"], pu["alpha"], pu["s1"], pu["s2"], n_iter, n_inter, n_mm, 2])})
+    np.savez_compressed(os.path.join(HERE, "image_golden_d20.npz"), **out)
+    print("images depth 20: psgla", out["psgla.X"].shape, out["psgla.M"].shape, "ula", out["ula.X"].shape, out["ula.M"].shape,
+          "ula delta %.3g lambd %.3g" % (pu["delta"], pu["lambd"]))
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
-    gmm2d()
-    images()
+    if "--only-d20" not in sys.argv:
+        gmm2d()
+        images()
+    images_depth20()

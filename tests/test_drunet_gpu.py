@@ -8,6 +8,9 @@ import torch.nn.functional as F
 import psgla_b200 as P
 
 pytestmark = pytest.mark.gpu
+# abs, per iterate: the non-residual U-Net feeds its whole output (|D| ~ 0.5, ~70 bf16 layers) into the iterate, unlike DnCNN's
+# small residual; set from the observed figures (pytest -s prints them)
+TOL_DRUNET = 2e-2
 
 
 def _bf(x):
@@ -155,8 +158,7 @@ def test_psgla_drunet_replay_against_oracle(drunets):
         Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
         torch.cuda.synchronize()
         assert len(Xr) == len(Xg) and len(Mr) == len(Mg) == len(M2g)
-        for a, b in zip(Xr + Mr, Xg + Mg):
-            assert (a - b).abs().max().item() < 2e-2
+        observed("DRUNet psgla iterate", max((a - b).abs().max().item() for a, b in zip(Xr + Mr, Xg + Mg)), TOL_DRUNET)
 
 
 def test_pnpula_drunet_replay_against_oracle(drunets):
@@ -177,8 +179,7 @@ def test_pnpula_drunet_replay_against_oracle(drunets):
     Xg, Mg, _ = P.pnpula(init, dg, pg, delta, lambd, n_iter=n_iter, n_inter=1, n_inter_mmse=1, seed=0, noise=noise)
     torch.cuda.synchronize()
     assert len(Xr) == len(Xg) and len(Mr) == len(Mg)
-    for a, b in zip(Xr + Mr, Xg + Mg):
-        assert (a - b).abs().max().item() < 2e-2
+    observed("DRUNet pnpula iterate", max((a - b).abs().max().item() for a, b in zip(Xr + Mr, Xg + Mg)), TOL_DRUNET)
 
 
 @pytest.mark.parametrize("family", ["dncnn", "drunet"])
@@ -200,9 +201,9 @@ def test_pnp_and_red_against_oracle(drunets, family):
     Xr, Fr, _ = io_.pnp(init, dg, "inpainting", net, device="cuda", **kw)
     Xg, Fg, Eg = P.pnp(init, dg, "inpainting", den, **kw)
     assert Eg == [] and len(Fg) == 1 and len(Xg) == len(Xr) == 22
-    assert max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)) < 2e-2
+    observed(family + " pnp iterate", max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)), TOL_DRUNET)
     kw = dict(lambd=torch.tensor(3000.0, device="cuda"), sig_float=s, delta=1e-5, n_iter=14)
     Xr, Fr, _ = io_.red(init, dg, "inpainting", net, device="cuda", **kw)
     Xg, Fg, Eg = P.red(init, dg, "inpainting", den, **kw)
     assert Eg == [] and len(Xg) == 14
-    assert max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)) < 2e-2
+    observed(family + " red iterate", max((a - b).abs().max().item() for a, b in zip(Xr + Fr, Xg + Fg)), TOL_DRUNET)

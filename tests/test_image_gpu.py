@@ -5,8 +5,9 @@ Stated tolerances
     (delta/lambd)/sigma^2 instead of the reference's divide-then-multiply);
   * one conv layer, bf16 operands with fp32 accumulation, bf16 output: <= 1 bf16 ulp of the output scale;
   * DnCNN residual (20 layers, bf16 activations): <= 1e-2 relative L2 error of the residual;
-  * sampler iterates under replayed noise, bf16 denoiser vs fp32 oracle: <= 2e-2 abs over the first 50 iterations
-    (images live in [0,1]); thinning / window bookkeeping must match exactly."""
+  * sampler iterates under replayed noise, bf16 denoiser vs fp32 oracle: <= 1e-3 abs per iterate (images live in [0,1];
+    observed 1e-4 .. 4e-4 over 50 .. 300 iterations with the Lipschitz-0.9 denoiser) and, where the denoiser term dominates
+    (large-gain weights), <= 2 % of the denoiser term itself; thinning / window bookkeeping must match exactly."""
 import os
 
 import numpy as np
@@ -16,9 +17,12 @@ import torch.nn.functional as F
 
 import psgla_b200 as P
 from oracle import image_oracle as io_
+from conftest import observed
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden.npz"))
+G20 = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden_d20.npz"))
+TOL_ITERATE = 1e-3  # abs, per iterate, bf16 tcgen05 denoiser vs the fp32 reference / oracle under the same noise
 
 
 @pytest.fixture(scope="module")
@@ -206,8 +210,7 @@ def test_psgla_replay_against_oracle(nets, problem):
     Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
     assert len(Xg) == len(Xr) == 10 and len(Mg) == len(Mr) == n_iter // (n_mm + 1) and len(M2g) == len(M2r)
     assert Xg[0].shape == Xr[0].shape == (3, 64, 64)
-    for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
-        assert (a - b).abs().max().item() < 2e-2
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
     # rng="torch" reproduces the reference's own generator stream on this device
     Xt, _, _ = P.psgla(init, dg, den, rng="torch", **kw)
     assert all(torch.equal(a, b) for a, b in zip(Xt, Xg))
@@ -229,8 +232,7 @@ def test_pnpula_replay_against_oracle(nets):
     Xg, Mg, M2g = P.pnp_ula(init, dg, P.PriorGrad(den, 1.0, prm["s1"], prm["s2"]), delta, lambd, n_iter=n_iter, n_inter=n_inter,
                             n_inter_mmse=n_mm, seed=2, noise=noise)
     assert len(Xg) == len(Xr) and len(Mg) == len(Mr)
-    for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
-        assert (a - b).abs().max().item() < 2e-2
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
 
 
 def test_golden_fixture_sampler_bookkeeping(nets):
@@ -276,7 +278,7 @@ def test_batched_chains_and_philox_mode(nets):
         P._lib.check(lib.psgla_img_noise(P._lib.ImgShape(1, 3, 32, 64), 0, 2, i, z.data_ptr(), None), "noise")
         zs.append(z)
     Xr, _, _ = io_.psgla(init, dg, net, device="cuda", noise=torch.stack(zs), **kw)
-    assert (Xr[-1] - X1[-1][0]).abs().max().item() < 2e-2
+    observed("philox replay through the oracle", (Xr[-1] - X1[-1][0]).abs().max().item(), TOL_ITERATE)
 
 
 def test_argument_errors(nets):
@@ -345,7 +347,7 @@ def test_final_psnr_ssim_parity_long_replay(nets):
     assert abs(a["ssim_mmse"].item() - b["ssim_mmse"].item()) < 1e-3
     assert (a["std"] - b["std"]).abs().max().item() < 5e-3
     assert (a["psnr_samples"] - b["psnr_samples"]).abs().max().item() < 0.1
-    assert max((u - v).abs().max().item() for u, v in zip(Xr, Xg)) < 2e-2  # per iterate, whole horizon
+    observed("300-iteration per-iterate error", max((u - v).abs().max().item() for u, v in zip(Xr, Xg)), TOL_ITERATE)
 
 
 def test_reference_edge_behaviours(nets, tmp_path):
@@ -420,3 +422,146 @@ def test_fused_next_pre_equals_separate_pre_kernel(weights, family, alg, rng, B,
         assert len(la) == len(lb) and len(la) > 0
         for ta, tb in zip(la, lb):
             assert torch.equal(ta, tb)
+
+
+def _d20_denoiser():
+    seed, n_pi, spatial = (int(v) for v in G20["weights"])
+    return io_.make_dncnn_weights(seed=seed, n_power_iter=n_pi, spatial=spatial)
+
+
+def test_reference_fixture_replayed_through_cuda():
+    """The UNMODIFIED reference's own outputs (tests/golden/image_golden_d20.npz: psgla on inpainting and pnpula with the
+    script's default table on deblurring, full DnCNN depth 20 / 64 features, CPU fp32) against the CUDA path fed the same mask /
+    observation / noise / weights: samples, window means and second moments within 1e-3, directly -- no oracle in between."""
+    den = P.DnCNN(pretrained=_d20_denoiser())
+    cu = lambda k: torch.from_numpy(G20[k]).cuda()  # noqa: E731
+    alpha, lambd, s, delta, n_iter, n_inter, n_mm = G20["psgla.params"]
+    dg = P.InpaintingDataGrad(cu("inp.mask"), cu("inp.y"), (1 / 255) ** 2)
+    X, M, M2 = P.psgla(cu("inp.init"), dg, den, float(alpha), float(lambd), float(s), float(delta), n_iter=int(n_iter),
+                       n_inter=int(n_inter), n_inter_mmse=int(n_mm), seed=7, noise=cu("psgla.noise"))
+    for got, key in ((X, "psgla.X"), (M, "psgla.M"), (M2, "psgla.M2")):
+        assert len(got) == G20[key].shape[0]
+        observed("reference fixture " + key, (torch.stack(got) - cu(key)).abs().max().item(), TOL_ITERATE)
+    # ... and rng="torch" on the CPU-seeded stream is NOT expected to match (CUDA generator), but the replay above is the
+    # reference's stream.  PnP-ULA, default parameters: delta ~ 1e-10, so delta * data_grad ~ 1e-6 and the noise step
+    # sqrt(2 delta) ~ 1.4e-5 sit a few fp32 ulps above X ~ 0.5 (6e-8); the prior term delta alpha / s2 = 0.11 carries the update.
+    delta, lambd, alpha, s1, s2, n_iter, n_inter, n_mm, l = G20["ula.params"]
+    dd = P.DeblurDataGrad(G20["deb.h"].reshape(-1), int(l), cu("deb.y"), (1 / 255) ** 2)
+    pg = P.PriorGrad(den, float(alpha), float(s1), float(s2))
+    X, M, M2 = P.pnpula(cu("deb.y"), dd, pg, torch.tensor(float(delta)), torch.tensor(float(lambd)), n_iter=int(n_iter),
+                        n_inter=int(n_inter), n_inter_mmse=int(n_mm), seed=11, noise=cu("ula.noise"))
+    for got, key in ((X, "ula.X"), (M, "ula.M"), (M2, "ula.M2")):
+        assert len(got) == G20[key].shape[0]
+        observed("reference fixture " + key, (torch.stack(got) - cu(key)).abs().max().item(), TOL_ITERATE)
+    assert (torch.stack(X)[-1] - cu("deb.y")[0]).abs().max().item() > 20 * TOL_ITERATE  # the chain has moved: not a vacuous match
+
+
+def test_pnpula_default_parameters_against_oracle(nets):
+    """The parameters the bench times (sampling_images.py:147-168 defaults: s1 = 2/255/255, lambd = 4.7e-10, delta = 1.05e-10) on
+    a 64 x 64 deblurring problem, 40 iterations, replayed noise, against the fp32 oracle."""
+    den, net = nets
+    torch.manual_seed(3)
+    im = torch.rand(1, 3, 64, 64, device="cuda")
+    dg, init, y = P.make_deblurring(im, l=4, blur_type="uniform")
+    prm = P.sampler_params("pnp_ula", den="DnCNN")
+    assert prm["delta"] < 1.1e-10 and prm["N"] == 100000 and prm["n_inter"] == 10
+    n_iter = 40
+    g = torch.Generator(device="cuda").manual_seed(5)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    delta = torch.tensor(prm["delta"], dtype=torch.float32, device="cuda")
+    lambd = torch.tensor(prm["lambd"], dtype=torch.float32, device="cuda")
+    ref_dg = lambda x: io_.deblur_data_grad(x, dg.h1d, 4, y, dg.sigma2)  # noqa: E731  the reference's conv2d formulation
+    pg_ref = io_.make_prior_grad(net, prm["alpha"], prm["s1"], prm["s2"], device="cuda")
+    Xr, Mr, M2r = io_.pnpula(init, ref_dg, pg_ref, delta, lambd, n_iter=n_iter, n_inter=4, n_inter_mmse=5, device="cuda", noise=noise)
+    Xg, Mg, M2g = P.pnp_ula(init, dg, P.PriorGrad(den, prm["alpha"], prm["s1"], prm["s2"]), delta, lambd, n_iter=n_iter, n_inter=4,
+                            n_inter_mmse=5, seed=5, noise=noise)
+    assert len(Xg) == len(Xr) == 10 and len(Mg) == len(Mr)
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+    assert (Xr[-1] - init[0]).abs().max().item() > 1e-3
+
+
+def test_large_gain_denoiser_term_dominates():
+    """Weights with per-layer gain ~0.93 (uniform +-2.3/sqrt(fan_in): the residual is ~25 % of the input instead of the 1e-3
+    of the Lipschitz-0.9 stand-in), so that the denoiser term carries the iterate: one PSGLA iteration from the same state must
+    reproduce the fp32 oracle's denoiser term X+ - Y to 2 % (bf16 activations through 20 layers), and 6 iterations stay within
+    2 % of the accumulated term."""
+    sd = P.random_dncnn_state_dict(11, 20, scale=2.3)
+    den = P.DnCNN(pretrained=sd)
+    net = io_.DnCNN().cuda()
+    net.load_state_dict(sd)
+    net.eval()
+    torch.manual_seed(6)
+    im = torch.rand(1, 3, 48, 64, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im)
+    prm = io_.resolve_params("psgla")
+    for n_iter in (1, 6):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+        kw = _psgla_kw(prm, n_iter, 1, 1, alpha=1.0)
+        Xr, _, _ = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw)
+        Xg, _, _ = P.psgla(init, dg, den, noise=noise, **kw)
+        # the denoiser's share of the total displacement: the run with the denoiser switched off (alpha = 0) is Y alone
+        kw0 = _psgla_kw(prm, n_iter, 1, 1, alpha=0.0)
+        Y0, _, _ = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw0)
+        term = (Xr[-1] - Y0[-1])
+        assert term.abs().mean().item() > 0.02  # it does dominate: the noise step is 0.011, the data step ~1e-3
+        observed("large-gain relative error of the denoiser term, %d it" % n_iter, ((Xg[-1] - Xr[-1]).norm() / term.norm()).item(), 2e-2)
+
+
+def test_dncnn_sampler_256_50_iterations_against_oracle(nets):
+    """BASELINE size: a 256 x 256 PSGLA run (DnCNN, inpainting, the script's parameters), 50 iterations under replayed noise,
+    every stored sample / window mean against the fp32 oracle on the same device."""
+    den, net = nets
+    torch.manual_seed(12)
+    low = torch.rand(1, 3, 20, 20, device="cuda")
+    im = F.interpolate(low, size=(256, 256), mode="bicubic", align_corners=False).clamp(0, 1)
+    dg, init, y, mask = P.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    prm = io_.resolve_params("psgla")
+    n_iter = 50
+    g = torch.Generator(device="cuda").manual_seed(9)
+    noise = torch.stack([torch.randn(im.shape, generator=g, device="cuda") for _ in range(n_iter)])
+    kw = _psgla_kw(prm, n_iter, 10, 10, alpha=1.0)
+    Xr, Mr, M2r = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw)
+    Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
+    assert len(Xg) == len(Xr) == 5 and len(Mg) == len(Mr) == 4
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+
+
+def test_statistics_only_mode_equals_the_stored_run(nets):
+    """store="stats" (no sample kept, window means folded on the device): Xlist is empty and the single returned mean / second
+    moment equal the average of the window means of the storing run; also: shape validation rejects what the kernels cannot index."""
+    den, _ = nets
+    torch.manual_seed(2)
+    im = torch.rand(1, 3, 32, 40, device="cuda")
+    dg, init, y, mask = P.make_inpainting(im)
+    kw = dict(alpha=1.0, lambd=5.0, sig_float=2 / 255, delta=(2 / 255) ** 2, n_iter=23, n_inter=2, n_inter_mmse=3, seed=4, n_chains=3)
+    X, M, M2 = P.psgla(init, dg, den, **kw)
+    Xs, Ms, M2s = P.psgla(init, dg, den, store="stats", **kw)
+    assert Xs == [] and len(Ms) == len(M2s) == 1 and len(M) == 23 // 4
+    assert (Ms[0] - torch.stack(M).mean(0)).abs().max().item() < 1e-6
+    assert (M2s[0] - torch.stack(M2).mean(0)).abs().max().item() < 1e-6
+    with pytest.raises(ValueError, match="colour image"):
+        P.psgla(torch.rand(1, 1, 32, 40, device="cuda"), dg, den, 1.0, 5.0, n_iter=10, seed=0)
+    with pytest.raises(ValueError, match="to match init"):
+        P.psgla(torch.rand(1, 3, 32, 48, device="cuda"), dg, den, 1.0, 5.0, n_iter=10, seed=0)
+    with pytest.raises(ValueError, match="n_iter"):
+        P.psgla(init, dg, den, 1.0, 5.0, n_iter=10, seed=0, noise=torch.zeros(4, 1, 3, 32, 40, device="cuda"))
+    with pytest.raises(ValueError, match="store"):
+        P.psgla(init, dg, den, 1.0, 5.0, n_iter=10, seed=0, store="none")
+
+
+def test_second_device_after_first():
+    """Per-device caches (function attributes, SM counts): the library used on cuda:0 and then on cuda:1 in one process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sd = _d20_denoiser()
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        den = P.DnCNN(pretrained=sd, device=dev)
+        x = torch.rand(1, 3, 40, 72, generator=torch.Generator().manual_seed(0)).to(dev)
+        outs.append(den.forward(x, 0.01).cpu())
+        D = P.Theorical_MMSE(*P.gaussian_mixt_example("cross"))
+        fin, _ = P.run_chains("psgla", 50, np.zeros(2), 0.3, np.eye(2), 1, D, 2 / 3, n_chains=4096, seed=0, device=dev)
+        outs.append(fin.cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])

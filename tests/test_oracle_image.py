@@ -210,3 +210,36 @@ def test_ssim_against_the_definition_window_by_window():
         per_channel.append(np.mean(vals))
     assert io_.ssim(a, b) == pytest.approx(float(np.mean(per_channel)), abs=1e-12)
     assert io_.psnr(a, b) == pytest.approx(10 * np.log10(1.0 / np.mean((a - b) ** 2)), abs=1e-12)
+
+
+def test_depth20_reference_fixture_pins_oracle_and_weight_regeneration():
+    """tests/golden/image_golden_d20.npz holds the UNMODIFIED reference's psgla / pnpula outputs with the full DnCNN (depth 20,
+    64 features; weights regenerated here from the seed).  The oracle must reproduce them on the CPU -- which pins, in one go, the
+    oracle loops, the operators, the script's default PnP-ULA table (delta ~ 1e-10) and the weight recipe the gpu tests use."""
+    G20 = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden_d20.npz"))
+    seed, n_pi, spatial = (int(v) for v in G20["weights"])
+    den = io_.DnCNN()
+    den.load_state_dict(io_.make_dncnn_weights(seed=seed, n_power_iter=n_pi, spatial=spatial))
+    den.eval()
+    im = torch.from_numpy(G20["im"])
+    inp = io_.make_inpainting(im, prop=0.5, sigma=1.0, seed_ip=0)
+    assert torch.equal(inp["mask"], torch.from_numpy(G20["inp.mask"])) and torch.equal(inp["y"], torch.from_numpy(G20["inp.y"]))
+    alpha, lambd, s, delta, n_iter, n_inter, n_mm = G20["psgla.params"]
+    X, M, M2 = io_.psgla(inp["init"], inp["data_grad"], den, torch.tensor(float(alpha)), torch.tensor(float(lambd)), float(s),
+                         float(delta), n_iter=int(n_iter), n_inter=int(n_inter), n_inter_mmse=int(n_mm), seed=7, device="cpu")
+    # 20 fp32 conv layers: thread count / SIMD width of the host may reorder sums, so 1e-6 instead of bit equality
+    for got, want in ((X, G20["psgla.X"]), (M, G20["psgla.M"]), (M2, G20["psgla.M2"])):
+        assert len(got) == want.shape[0]
+        assert np.abs(torch.stack(got).numpy() - want).max() < 1e-6
+    deb = io_.make_deblurring(im, l=2, blur_type="gaussian", si=1.0, sigma=1.0, seed_ip=0)
+    delta, lambd, alpha, s1, s2, n_iter, n_inter, n_mm, l = G20["ula.params"]
+    pu = io_.resolve_params("pnp_ula")
+    assert (pu["delta"], pu["lambd"], pu["s1"], pu["s2"]) == (float(delta), float(lambd), float(s1), float(s2))
+    assert 1.0e-10 < delta < 1.1e-10  # the script's default: s = 2/255 divided by 255 once more (sampling_images.py:149-153)
+    pg = io_.make_prior_grad(den, float(alpha), float(s1), float(s2))
+    X, M, M2 = io_.pnpula(deb["init"], deb["data_grad"], pg, torch.tensor(float(delta), dtype=torch.float32),
+                          torch.tensor(float(lambd), dtype=torch.float32), n_iter=int(n_iter), n_inter=int(n_inter),
+                          n_inter_mmse=int(n_mm), seed=11, device="cpu")
+    for got, want in ((X, G20["ula.X"]), (M, G20["ula.M"]), (M2, G20["ula.M2"])):
+        assert len(got) == want.shape[0]
+        assert np.abs(torch.stack(got).numpy() - want).max() < 1e-6

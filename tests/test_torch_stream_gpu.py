@@ -93,7 +93,7 @@ def test_seed_only_drop_in_against_the_reference_algorithm_on_cuda(problem):
     """The drop-in property the torch stream buys: the reference algorithm (oracle restatement, bit-identical to the
     unmodified reference on the CPU, run here on cuda with ITS OWN torch.Generator(seed)) and psgla(..., seed=seed,
     rng="torch_cuda") consume the same noise without any tensor crossing between them; what remains is the bf16 denoiser
-    against the fp32 one.  Tolerance 2e-2 abs on iterates in [0, 1] over 6 iterations (observed ~1e-4), bookkeeping exact."""
+    against the fp32 one.  Tolerance 1e-3 abs on iterates in [0, 1] over 6 iterations (observed ~1e-4), bookkeeping exact."""
     sd = io_.make_dncnn_weights(seed=0, n_power_iter=5, spatial=16)
     den = P.DnCNN(pretrained=sd)
     net = io_.DnCNN().cuda()
@@ -112,7 +112,7 @@ def test_seed_only_drop_in_against_the_reference_algorithm_on_cuda(problem):
     torch.cuda.synchronize()
     assert len(Xr) == len(Xg) == 3 and len(Mr) == len(Mg) == 2 and len(M2r) == len(M2g) == 2
     for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g):
-        assert (a - b).abs().max().item() < 2e-2
+        assert (a - b).abs().max().item() < 1e-3
     # and the noise really is the same: with a different seed the iterates differ at the noise scale
     Xo, _, _ = P.psgla(init, dg, den, rng="torch_cuda", **dict(kw, seed=6))
     assert (Xo[0] - Xg[0]).abs().max().item() > 1e-2
