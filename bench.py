@@ -591,7 +591,7 @@ def bench_image_deblur(args, P, torch, rank, ws, dev, peaks):
     pre_ms, _ = timer.total_ms()
     pre_launch_ms = pre_ms / reps
     px = B * H * Wd
-    # blur_kernel_t<true,4>: reads X and y, writes base (fp32, 12 B per pixel-channel) + the bf16 NHWC16 denoiser input (32 B/px)
+    # deblur_ata_kernel<8>: reads X and A^T y, writes base (fp32, 12 B per pixel-channel) + the bf16 NHWC16 denoiser input (32 B/px)
     pre_bytes = (12 * 3 + 32) * px
     step_tflops = DNCNN_FLOP_PER_PIXEL * px * K / (total_ms * 1e-3) / 1e12
     return {
@@ -604,8 +604,9 @@ def bench_image_deblur(args, P, torch, rank, ws, dev, peaks):
         "dtype": "bf16 activations / fp32 accumulate, fp32 state", "gpu_launches": 21 * K,
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
-        "pre_kernel": {"kernel": "blur_kernel_t<true,4> (A^T(Ax - y) as a shared-memory staged separable circular stencil + "
-                                 "projection + noise)", "bound": "hbm", "achieved": pre_bytes / (pre_launch_ms * 1e-3) / 1e9,
+        "pre_kernel": {"kernel": ("blur_kernel_t<true,4> (four 9-tap passes, PSGLA_BLUR_4PASS=1)" if run.aty is None else
+                                  "deblur_ata_kernel<8> ((A^T A) x - A^T y: row-streaming separable 17-tap stencil, A^T y precomputed, "
+                                  "+ projection + noise)"), "bound": "hbm", "achieved": pre_bytes / (pre_launch_ms * 1e-3) / 1e9,
                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": pre_bytes / (pre_launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": pre_launch_ms,
                        "algorithmic_bytes_per_pixel": 12 * 3 + 32},

@@ -177,6 +177,13 @@ int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape shape, cons
 int psgla_img_pre_deblur(const psgla_pre_params* p, psgla_img_shape shape, const float* x_dev, const float* h1d_host,
                          int l, const float* y_dev, int y_B, const float* noise_dev, float* base_dev,
                          void* den_in_dev, void* stream);
+/* The same step in its A^T A form: A^T(A x - y) = (A^T A) x - A^T y.  A^T A is the separable circular (4l+1)-tap stencil with
+ * taps h * h, and aty_dev = A^T y = psgla_img_blur(y) is computed ONCE per run by the caller ([1 or B][C][H][W] fp32): one
+ * horizontal and one vertical pass over x per iteration, done as a row-streaming filter (vertical window in registers).  Same
+ * results as psgla_img_pre_deblur up to fp32 rounding (2e-5 relative in the tests).  Half-widths l = 1..4. */
+int psgla_img_pre_deblur_ata(const psgla_pre_params* p, psgla_img_shape shape, const float* x_dev, const float* h1d_host,
+                             int l, const float* aty_dev, int aty_B, const float* noise_dev, float* base_dev,
+                             void* den_in_dev, void* stream);
 /* y = A x alone (builds the observation, sampling_images.py:335). */
 int psgla_img_blur(psgla_img_shape shape, const float* x_dev, const float* h1d_host, int l, float* out_dev,
                    void* stream);

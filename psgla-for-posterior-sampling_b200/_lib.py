@@ -73,6 +73,8 @@ SIGNATURES = {
     "psgla_img_pre_inpaint": (_int, [C.POINTER(PreParams), ImgShape, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp, _vp]),
     "psgla_img_pre_deblur": (_int, [C.POINTER(PreParams), ImgShape, _vp, C.POINTER(C.c_float), _int, _vp, _int, _vp,
                                     _vp, _vp, _vp]),
+    "psgla_img_pre_deblur_ata": (_int, [C.POINTER(PreParams), ImgShape, _vp, C.POINTER(C.c_float), _int, _vp, _int, _vp,
+                                        _vp, _vp, _vp]),
     "psgla_img_blur": (_int, [ImgShape, _vp, C.POINTER(C.c_float), _int, _vp, _vp]),
     "psgla_img_noise": (_int, [ImgShape, _u64, _i64, _i64, _vp, _vp]),
     "psgla_torch_cuda_randn_policy": (_int, [_i64, _int, _int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),

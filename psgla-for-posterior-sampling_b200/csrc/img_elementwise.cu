@@ -82,7 +82,11 @@ pre_inpaint_kernel(PreArgs a, int B, int H, int W, const float* __restrict__ x, 
 //   taps are symmetric by construction, sampling_images.py:306-314).
 constexpr int BT = 32;
 constexpr int MAX_L = 16;
-__constant__ float c_taps[2 * MAX_L + 1];
+// The taps travel BY VALUE in the kernel arguments (they then sit in the constant bank as FMA operands): a __constant__
+// symbol would be one array per device, shared -- and raced on -- by every stream and host thread that blurs with other taps.
+struct Taps {
+  float v[2 * MAX_L + 1];
+};
 
 // i mod n for i in [-n, 2n) by one conditional correction; the general case (tiny images, halo wider than the image)
 // falls back to the remainder.
@@ -99,7 +103,7 @@ __device__ __forceinline__ int wrap(int i, int n) {
 // All loops below are (row = warp, warp + 8, ...; column = lane, lane + 32, ...): no integer division in the hot path.
 template <bool FULL>  // FULL: Langevin pre; else: out = A x
 __global__ void __launch_bounds__(256)
-blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, const float* __restrict__ y, int y_B,
+blur_kernel(PreArgs a, const Taps c_taps_arg, int B, int H, int W, int l, const float* __restrict__ x, const float* __restrict__ y, int y_B,
             const float* __restrict__ noise, float* __restrict__ out, __nv_bfloat16* __restrict__ den_in) {
   extern __shared__ float sm[];
   const int halo = FULL ? 2 * l : l;
@@ -133,7 +137,7 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
       for (int cc = lane; cc < w1; cc += 32) {
         const float* src = s0 + r * SW + cc;
         float acc = 0.f;
-        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t], acc);
+        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps_arg.v[t], src[t], acc);
         s1[r * SW + cc] = acc;
       }
     __syncthreads();
@@ -144,7 +148,7 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
       for (int cc = lane; cc < w1; cc += 32) {
         const float* src = s1 + r * SW + cc;
         float acc = 0.f;
-        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t * SW], acc);
+        for (int t = 0; t < nt; ++t) acc = fmaf(c_taps_arg.v[t], src[t * SW], acc);
         if (FULL) acc -= yp[yrow + wrap(x0 - l + cc, W)];
         s0[r * SW + cc] = acc;
       }
@@ -164,7 +168,7 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
     for (int r = warp; r < h1; r += 8) {
       const float* src = s0 + r * SW + lane;  // BT == 32 columns: one per lane
       float acc = 0.f;
-      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t], acc);
+      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps_arg.v[t], src[t], acc);
       s1[r * SW + lane] = acc;
     }
     __syncthreads();
@@ -172,7 +176,7 @@ blur_kernel(PreArgs a, int B, int H, int W, int l, const float* __restrict__ x, 
     for (int j = 0; j < 4; ++j) {
       const float* src = s1 + prow * SW + pcol + j;
       float acc = 0.f;
-      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps[t], src[t * SW], acc);
+      for (int t = 0; t < nt; ++t) acc = fmaf(c_taps_arg.v[t], src[t * SW], acc);
       res[c][j] = acc;
     }
   }
@@ -219,7 +223,7 @@ struct BlurCfg {
 
 template <bool FULL, int L>
 __global__ void __launch_bounds__(256, 3)
-blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const float* __restrict__ y, int y_B,
+blur_kernel_t(PreArgs a, const Taps c_taps_arg, int B, int H, int W, const float* __restrict__ x, const float* __restrict__ y, int y_B,
               const float* __restrict__ noise, float* __restrict__ out, __nv_bfloat16* __restrict__ den_in) {
   using Cfg = BlurCfg<FULL, L>;
   constexpr int HALO = Cfg::HALO, SW = Cfg::SW, W1 = Cfg::W1;
@@ -241,7 +245,7 @@ blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const
   const int prow = tid >> 3, pcol = (tid & 7) * 4;  // final owner: row prow, columns pcol..pcol+3 of the tile
   float h[NT];
 #pragma unroll
-  for (int t = 0; t < NT; ++t) h[t] = c_taps[t];
+  for (int t = 0; t < NT; ++t) h[t] = c_taps_arg.v[t];
   // wrapped global columns of this lane's staged columns (lane, lane + 32, lane + 64)
   int gxs[3], gys[3];
 #pragma unroll
@@ -432,6 +436,185 @@ blur_kernel_t(PreArgs a, int B, int H, int W, const float* __restrict__ x, const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ deblur pre, A^T A form
+// A and A^T are the same symmetric separable circular operator (sampling_images.py:306-330; flip(h_) == h_ bit for bit), so
+//   A^T(A x - y) = (A^T A) x - A^T y,   A^T A separable with the 1-D taps k = h * h (4l + 1 of them),
+// and A^T y does not change during a run: the caller blurs y once (psgla_img_blur) and hands it in.  What is left per
+// iteration is ONE horizontal and ONE vertical (4l + 1)-tap pass over x, done here as a row-streaming filter:
+//   * a block of 192 threads owns a strip of 256 columns (the whole row of a 256-wide image: no horizontal halo) of all three
+//     channels and walks RH + 4l input rows top to bottom; thread (channel, quad q) owns 4 consecutive columns;
+//   * input rows arrive through a 4-deep cp.async ring in shared memory (wrap-around indices precomputed per thread);
+//   * the horizontal pass is register-tiled (4 outputs from 4 + 4l staged values: five 16-byte shared loads for 68 FMAs);
+//   * the vertical pass never touches shared memory: each thread keeps the last 4l + 1 horizontally filtered rows of its 4
+//     columns in registers (the row loop is unrolled by 4l + 1 so that the ring is statically indexed);
+//   * the Langevin step, the noise draw and the fp32 base store happen in the thread that owns the pixel; the bf16 NHWC16
+//     denoiser input needs the three channels of a pixel together and is written one row late by the channel-0 threads from
+//     a double-buffered shared-memory row.
+// Per pixel-channel: 2 (4l + 1) FMAs against the 4-pass kernel's ~50 at l = 4 -- but what the 4-pass kernel really lost its
+// time on was five block-wide barriers per channel-tile and a 2.25x read amplification; here it is two barriers per ROW and
+// (RH + 4l) / RH.  Results differ from the two-pass-of-A formulation by fp32 rounding only (tests: 2e-5 relative).
+constexpr int ATA_THREADS = 192;
+constexpr int ATA_COLS = 256;   // strip width: 64 quads of 4 columns
+constexpr int ATA_NBUF = 4;     // cp.async ring depth (rows)
+struct Taps2 {
+  float v[4 * 4 + 1];  // k = h * h for l <= 4
+};
+
+template <int K2>  // K2 = 2 l: half-width of A^T A
+__global__ void __launch_bounds__(ATA_THREADS, 2)
+deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const float* __restrict__ x,
+                  const float* __restrict__ aty, int aty_B, const float* __restrict__ noise, float* __restrict__ out,
+                  __nv_bfloat16* __restrict__ den_in) {
+  constexpr int NT = 2 * K2 + 1;         // taps
+  constexpr int SROW = ATA_COLS + 2 * K2;  // staged columns per channel
+  constexpr int ROWSET = 3 * SROW;       // floats of one staged row (3 channels)
+  constexpr int NE = (ROWSET + ATA_THREADS - 1) / ATA_THREADS;
+  __shared__ __align__(16) float ring[ATA_NBUF][ROWSET];
+  __shared__ __align__(16) float xin_s[2][3][ATA_COLS];
+  const int tid = threadIdx.x;
+  const int ch = tid >> 6, q = tid & 63;
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * ATA_COLS, y0 = blockIdx.y * RH;
+  const int rh = min(RH, H - y0);        // output rows of this block
+  const int nrows = rh + 2 * K2;         // input rows it walks
+  const long long plane = (long long)H * W;
+  const float* xb = x + (long long)b * 3 * plane;
+  // this thread's staged elements: e = tid + 192 i  ->  (channel, staged column); global offset without the row term
+  unsigned goff[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int e = tid + ATA_THREADS * i;
+    const int c = e / SROW, col = e - c * SROW;
+    goff[i] = (e < ROWSET) ? (unsigned)((long long)c * plane + wrap(x0 - K2 + col, W)) : 0u;
+  }
+  auto stage = [&](int r) {
+    if (r < nrows) {
+      const long long rowoff = (long long)wrap(y0 - K2 + r, H) * W;
+      float* dst = ring[r % ATA_NBUF];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int e = tid + ATA_THREADS * i;
+        if (e < ROWSET) {
+          const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + e);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(xb + rowoff + goff[i]) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int r = 0; r < ATA_NBUF - 1; ++r) stage(r);
+
+  const int gx0 = x0 + 4 * q;
+  const bool vec_ok = (W % 4 == 0) && gx0 + 3 < W;
+  float hring[NT][4];  // horizontally filtered rows r - 2 K2 .. r of this thread's 4 columns
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hring[t][j] = 0.f;
+
+  // den_in of output row `orow` (tile-local), written by the channel-0 threads once all three channels are in xin_s
+  auto flush_den_in = [&](int orow) {
+    if (ch == 0 && gx0 < W) {
+      const int gy = y0 + orow;
+      const float(*xs)[ATA_COLS] = xin_s[orow & 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gx0 + j < W)
+          store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx0 + j) * 16, xs[0][4 * q + j], xs[1][4 * q + j],
+                       xs[2][4 * q + j], a.den_in_c3);
+    }
+  };
+
+  for (int r0 = 0; r0 < nrows; r0 += NT) {
+#pragma unroll
+    for (int ph = 0; ph < NT; ++ph) {
+      const int r = r0 + ph;
+      if (r < nrows) {  // block-uniform
+        asm volatile("cp.async.wait_group %0;" ::"n"(ATA_NBUF - 2) : "memory");
+        __syncthreads();           // row r is visible; everyone is done with row r - 1 (its buffer is restaged next)
+        stage(r + ATA_NBUF - 1);
+        if (r > 2 * K2) flush_den_in(r - 2 * K2 - 1);  // the previous output row's xin_s is complete
+        // ---- horizontal pass on row r
+        {
+          const float4* src4 = reinterpret_cast<const float4*>(ring[r % ATA_NBUF] + ch * SROW + 4 * q);
+          float in[4 + 2 * K2];
+#pragma unroll
+          for (int v = 0; v < (4 + 2 * K2) / 4; ++v) {
+            const float4 t = src4[v];
+            in[4 * v] = t.x, in[4 * v + 1] = t.y, in[4 * v + 2] = t.z, in[4 * v + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], in[j + t], acc);
+            hring[ph][j] = acc;
+          }
+        }
+        // ---- vertical pass + Langevin step for output row r - 2 K2
+        if (r >= 2 * K2) {
+          const int orow = r - 2 * K2;
+          const int gy = y0 + orow;
+          float g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], hring[(ph + 1 + t) % NT][j], acc);  // rows r - 2 K2 + t
+            g[j] = acc;
+          }
+          float xin[4] = {0.f, 0.f, 0.f, 0.f};
+          if (gx0 < W) {
+            const long long e0 = (long long)ch * plane + (long long)gy * W + gx0;  // element index inside the chain
+            const long long gi0 = (long long)b * 3 * plane + e0;
+            const long long ai0 = (long long)(aty_B > 1 ? b : 0) * 3 * plane + e0;
+            float xv[4], av[4], z[4];
+            if (vec_ok) {
+              const float4 t0 = *reinterpret_cast<const float4*>(x + gi0);
+              const float4 t1 = *reinterpret_cast<const float4*>(aty + ai0);
+              xv[0] = t0.x, xv[1] = t0.y, xv[2] = t0.z, xv[3] = t0.w;
+              av[0] = t1.x, av[1] = t1.y, av[2] = t1.z, av[3] = t1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                xv[j] = (gx0 + j < W) ? x[gi0 + j] : 0.f;
+                av[j] = (gx0 + j < W) ? aty[ai0 + j] : 0.f;
+              }
+            }
+            if (noise) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) z[j] = (gx0 + j < W) ? noise[gi0 + j] : 0.f;
+            } else if ((e0 & 3) == 0) {
+              draw_quad(a, b, (uint32_t)e0, z);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) z[j] = draw_at(a, b, (uint32_t)(e0 + j));
+            }
+            float bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              bv[j] = langevin_base(a, xv[j], g[j] - av[j], z[j]);
+              xin[j] = (a.alg == PSGLA_ALG_PNPULA) ? xv[j] : bv[j];
+            }
+            if (vec_ok) {
+              *reinterpret_cast<float4*>(out + gi0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (gx0 + j < W) out[gi0 + j] = bv[j];
+            }
+          }
+          *reinterpret_cast<float4*>(&xin_s[orow & 1][ch][4 * q]) = make_float4(xin[0], xin[1], xin[2], xin[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  flush_den_in(rh - 1);
+}
+
 __global__ void __launch_bounds__(256)
 noise_kernel(int B, long long chw, unsigned long long seed, long long chain_id0, unsigned int iteration,
              float* __restrict__ out) {
@@ -499,20 +682,10 @@ static int check_img(const psgla_img_shape& s) {
   return PSGLA_OK;
 }
 
-// The taps live in constant memory.  A sampler passes the same taps every iteration, so the (stream-ordered) upload is
-// skipped when the host values equal the ones uploaded last on this device by this thread.
-static int upload_taps(const float* h1d_host, int l, cudaStream_t st) {
+static int make_taps(const float* h1d_host, int l, Taps* t) {
   PSGLA_REQUIRE(h1d_host != nullptr && l >= 0 && l <= MAX_L, "blur half-width l must be in 0..%d (got %d)", MAX_L, l);
-  static thread_local float last[2 * MAX_L + 1];
-  static thread_local int last_l = -1, last_dev = -1;
-  static thread_local cudaStream_t last_stream = nullptr;
-  int dev = 0;
-  PSGLA_CUDA_TRY(cudaGetDevice(&dev));
-  const int n = 2 * l + 1;
-  if (dev == last_dev && l == last_l && st == last_stream && memcmp(last, h1d_host, sizeof(float) * n) == 0) return PSGLA_OK;
-  PSGLA_CUDA_TRY(cudaMemcpyToSymbolAsync(c_taps, h1d_host, sizeof(float) * n, 0, cudaMemcpyHostToDevice, st));
-  memcpy(last, h1d_host, sizeof(float) * n);
-  last_l = l, last_dev = dev, last_stream = st;
+  std::memset(t, 0, sizeof(*t));
+  std::memcpy(t->v, h1d_host, sizeof(float) * (2 * l + 1));
   return PSGLA_OK;
 }
 
@@ -549,8 +722,8 @@ extern "C" int psgla_img_pre_inpaint(const psgla_pre_params* p, psgla_img_shape 
 }
 
 template <bool FULL, int L>
-static int launch_blur_t(const PreArgs& a, psgla_img_shape s, const float* x, const float* y, int y_B, const float* noise,
-                         float* out, void* den_in, cudaStream_t st) {
+static int launch_blur_t(const PreArgs& a, const Taps& taps, psgla_img_shape s, const float* x, const float* y, int y_B,
+                         const float* noise, float* out, void* den_in, cudaStream_t st) {
   constexpr size_t smem = BlurCfg<FULL, L>::SMEM;
   static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
   const unsigned long long dev_bit = 1ull << (current_device() & 63);
@@ -559,31 +732,28 @@ static int launch_blur_t(const PreArgs& a, psgla_img_shape s, const float* x, co
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int tiles = ((s.W + BT - 1) / BT) * ((s.H + BT - 1) / BT);
-  blur_kernel_t<FULL, L><<<dim3(tiles, s.B), 256, smem, st>>>(a, s.B, s.H, s.W, x, y, y_B, noise, out, (__nv_bfloat16*)den_in);
+  blur_kernel_t<FULL, L><<<dim3(tiles, s.B), 256, smem, st>>>(a, taps, s.B, s.H, s.W, x, y, y_B, noise, out, (__nv_bfloat16*)den_in);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
 }
 
 template <bool FULL>
-static int launch_blur(const PreArgs& a, psgla_img_shape s, int l, const float* x, const float* y, int y_B,
+static int launch_blur(const PreArgs& a, const Taps& taps, psgla_img_shape s, int l, const float* x, const float* y, int y_B,
                        const float* noise, float* out, void* den_in, cudaStream_t st) {
   switch (l) {  // compile-time even half-widths (the reference's default is l = 4); anything else takes the generic kernel
-    case 2: return launch_blur_t<FULL, 2>(a, s, x, y, y_B, noise, out, den_in, st);
-    case 4: return launch_blur_t<FULL, 4>(a, s, x, y, y_B, noise, out, den_in, st);
-    case 6: return launch_blur_t<FULL, 6>(a, s, x, y, y_B, noise, out, den_in, st);
-    case 8: return launch_blur_t<FULL, 8>(a, s, x, y, y_B, noise, out, den_in, st);
+    case 2: return launch_blur_t<FULL, 2>(a, taps, s, x, y, y_B, noise, out, den_in, st);
+    case 4: return launch_blur_t<FULL, 4>(a, taps, s, x, y, y_B, noise, out, den_in, st);
+    case 6: return launch_blur_t<FULL, 6>(a, taps, s, x, y, y_B, noise, out, den_in, st);
+    case 8: return launch_blur_t<FULL, 8>(a, taps, s, x, y, y_B, noise, out, den_in, st);
     default: break;
   }
   const int halo = FULL ? 2 * l : l;
   const int SW = BT + 2 * halo;
   const size_t smem = (size_t)2 * SW * SW * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (smem > 48 * 1024)  // a per-device attribute of the function, cheap to set: no process-wide cache
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(blur_kernel<FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   const int tiles = ((s.W + BT - 1) / BT) * ((s.H + BT - 1) / BT);
-  blur_kernel<FULL><<<dim3(tiles, s.B), 256, smem, st>>>(a, s.B, s.H, s.W, l, x, y, y_B, noise, out,
+  blur_kernel<FULL><<<dim3(tiles, s.B), 256, smem, st>>>(a, taps, s.B, s.H, s.W, l, x, y, y_B, noise, out,
                                                         (__nv_bfloat16*)den_in);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
@@ -601,9 +771,65 @@ extern "C" int psgla_img_pre_deblur(const psgla_pre_params* p, psgla_img_shape s
   PSGLA_REQUIRE(x_dev != base_dev, "psgla_img_pre_deblur: base must not alias x (the stencil reads neighbours)");
   PSGLA_REQUIRE(y_B == 1 || y_B == s.B, "y_B must be 1 or B");
   a.chw = 3LL * s.H * s.W;
-  rc = upload_taps(h1d_host, l, (cudaStream_t)stream);
+  Taps taps;
+  rc = make_taps(h1d_host, l, &taps);
   if (rc) return rc;
-  return launch_blur<true>(a, s, l, x_dev, y_dev, y_B, noise_dev, base_dev, den_in_dev, (cudaStream_t)stream);
+  return launch_blur<true>(a, taps, s, l, x_dev, y_dev, y_B, noise_dev, base_dev, den_in_dev, (cudaStream_t)stream);
+}
+
+// k = h * h (full 1-D convolution, 4 l + 1 taps) in double, rounded once.
+static void ata_taps(const float* h, int l, Taps2* k) {
+  std::memset(k, 0, sizeof(*k));
+  const int n = 2 * l + 1;
+  for (int i = 0; i < 2 * n - 1; ++i) {
+    double acc = 0;
+    for (int j = 0; j < n; ++j)
+      if (i - j >= 0 && i - j < n) acc += (double)h[j] * (double)h[i - j];
+    k->v[i] = (float)acc;
+  }
+}
+
+template <int K2>
+static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const float* x, const float* aty, int aty_B,
+                      const float* noise, float* out, void* den_in, cudaStream_t st) {
+  // rows per block: the busiest SM holds ceil(blocks / SMs) blocks of RH + 2 K2 row steps each
+  const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = num_sms();
+  int best_rh = 16;
+  long long best = -1;
+  for (int rh = 8; rh <= 128; rh *= 2) {
+    const long long blocks = (long long)strips * ((s.H + rh - 1) / rh) * s.B;
+    const long long cost = ((blocks + sms - 1) / sms) * (rh + 2 * K2);
+    if (best < 0 || cost < best) best = cost, best_rh = rh;
+  }
+  PSGLA_REQUIRE(s.B <= 65535 && (s.H + best_rh - 1) / best_rh <= 65535, "too many chains / rows for one launch");
+  deblur_ata_kernel<K2><<<dim3(strips, (s.H + best_rh - 1) / best_rh, s.B), ATA_THREADS, 0, st>>>(
+      a, k, s.B, s.H, s.W, best_rh, x, aty, aty_B, noise, out, (__nv_bfloat16*)den_in);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_img_pre_deblur_ata(const psgla_pre_params* p, psgla_img_shape s, const float* x_dev,
+                                        const float* h1d_host, int l, const float* aty_dev, int aty_B,
+                                        const float* noise_dev, float* base_dev, void* den_in_dev, void* stream) {
+  PreArgs a;
+  int rc = fill_pre(p, &a);
+  if (rc) return rc;
+  rc = check_img(s);
+  if (rc) return rc;
+  PSGLA_REQUIRE(x_dev && aty_dev && base_dev && den_in_dev && h1d_host, "psgla_img_pre_deblur_ata: null pointer");
+  PSGLA_REQUIRE(x_dev != base_dev, "psgla_img_pre_deblur_ata: base must not alias x (the stencil reads neighbours)");
+  PSGLA_REQUIRE(aty_B == 1 || aty_B == s.B, "aty_B must be 1 or B");
+  PSGLA_REQUIRE(l >= 1 && l <= 4, "psgla_img_pre_deblur_ata serves half-widths 1..4 (got %d); use psgla_img_pre_deblur", l);
+  a.chw = 3LL * s.H * s.W;
+  Taps2 k;
+  ata_taps(h1d_host, l, &k);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (l) {
+    case 1: return launch_ata<2>(a, k, s, x_dev, aty_dev, aty_B, noise_dev, base_dev, den_in_dev, st);
+    case 2: return launch_ata<4>(a, k, s, x_dev, aty_dev, aty_B, noise_dev, base_dev, den_in_dev, st);
+    case 3: return launch_ata<6>(a, k, s, x_dev, aty_dev, aty_B, noise_dev, base_dev, den_in_dev, st);
+    default: return launch_ata<8>(a, k, s, x_dev, aty_dev, aty_B, noise_dev, base_dev, den_in_dev, st);
+  }
 }
 
 extern "C" int psgla_img_blur(psgla_img_shape s, const float* x_dev, const float* h1d_host, int l, float* out_dev,
@@ -611,10 +837,11 @@ extern "C" int psgla_img_blur(psgla_img_shape s, const float* x_dev, const float
   int rc = check_img(s);
   if (rc) return rc;
   PSGLA_REQUIRE(x_dev && out_dev && x_dev != out_dev, "psgla_img_blur: null or aliased pointer");
-  rc = upload_taps(h1d_host, l, (cudaStream_t)stream);
+  Taps taps;
+  rc = make_taps(h1d_host, l, &taps);
   if (rc) return rc;
   PreArgs a{};
-  return launch_blur<false>(a, s, l, x_dev, nullptr, 1, nullptr, out_dev, nullptr, (cudaStream_t)stream);
+  return launch_blur<false>(a, taps, s, l, x_dev, nullptr, 1, nullptr, out_dev, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int psgla_img_noise(psgla_img_shape s, uint64_t seed, int64_t chain_id0, int64_t iteration, float* out_dev,

@@ -15,8 +15,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["DnCNN", "DRUNet", "random_dncnn_state_dict", "lipschitz_dncnn_state_dict", "random_drunet_state_dict",
-           "DRUNET_KEYS"]
+__all__ = ["DnCNN", "DRUNet", "random_dncnn_state_dict", "lipschitz_dncnn_state_dict", "smoothing_dncnn_state_dict",
+           "random_drunet_state_dict", "DRUNET_KEYS"]
 
 
 def random_dncnn_state_dict(seed=0, depth=20, nf=64, scale=1.0):
@@ -61,6 +61,38 @@ def lipschitz_dncnn_state_dict(seed=0, depth=20, nf=64, lipschitz=0.9, spatial=1
     for name in ["in_conv"] + ["conv_list.%d" % i for i in range(depth - 2)] + ["out_conv"]:
         w = sd[name + ".weight"]
         sd[name + ".weight"] = (w * (per_layer / _conv_operator_norm(w, spatial))).float()
+    return sd
+
+
+def smoothing_dncnn_state_dict(eps=0.5, n_smooth=6, depth=20, nf=64):
+    """A DnCNN-architecture state dict, written down by hand, that IS a (weak) denoiser: its residual is
+    ``R(x) = eps * (G x - x)`` with G = ``n_smooth`` passes of the 3 x 3 binomial kernel [1 2 1]^T [1 2 1] / 16.  The checkpoint the
+    reference uses cannot be fetched offline and a random-init network restores nothing (unobserved pixels random-walk), so
+    this is the stand-in for runs whose PSNR should MEAN something: PSGLA with it is diffusion inpainting / smoothing-regularised
+    deblurring, stable at any length, and ||R||_Lip <= eps < 1.  Construction (ReLU networks compute linear maps on
+    x = relu(x) - relu(-x)): features 0-2 / 3-5 carry relu(+-x) and are smoothed by layers 1..n_smooth, features 6-8 / 9-11
+    carry relu(+-x) unchanged, every other feature is zero; the last layer forms eps ((f0-2 - f3-5) - (f6-8 - f9-11))."""
+    if depth < n_smooth + 2 or nf < 12:
+        raise ValueError("needs depth >= n_smooth + 2 and nf >= 12")
+    g1 = torch.tensor([1.0, 2.0, 1.0]) / 4.0
+    G = torch.outer(g1, g1)
+    ident = torch.zeros(3, 3)
+    ident[1, 1] = 1.0
+    sd = {}
+    w = torch.zeros(nf, 3, 3, 3)
+    for c in range(3):
+        for base, sign in ((0, 1.0), (3, -1.0), (6, 1.0), (9, -1.0)):
+            w[base + c, c, 1, 1] = sign
+    sd["in_conv.weight"], sd["in_conv.bias"] = w, torch.zeros(nf)
+    for i in range(depth - 2):
+        w = torch.zeros(nf, nf, 3, 3)
+        for f in range(12):
+            w[f, f] = G if (f < 6 and i < n_smooth) else ident
+        sd["conv_list.%d.weight" % i], sd["conv_list.%d.bias" % i] = w, torch.zeros(nf)
+    w = torch.zeros(3, nf, 3, 3)
+    for c in range(3):
+        w[c, c, 1, 1], w[c, 3 + c, 1, 1], w[c, 6 + c, 1, 1], w[c, 9 + c, 1, 1] = eps, -eps, -eps, eps
+    sd["out_conv.weight"], sd["out_conv.bias"] = w, torch.zeros(3)
     return sd
 
 

@@ -134,6 +134,11 @@ class _Run:
         if isinstance(data_grad, DeblurDataGrad):
             self.y = operand(data_grad.y, "the blurred observation y", (3,))
             self.mask = None
+            # A^T(A x - y) = (A^T A) x - A^T y: A^T y is blurred once here, the iterations run the two-pass A^T A kernel
+            # (PSGLA_BLUR_4PASS=1 keeps the four-pass kernel for A/B runs; half-widths above 4 always take it)
+            self.aty = None
+            if 1 <= data_grad.l <= 4 and os.environ.get("PSGLA_BLUR_4PASS", "0") != "1":
+                self.aty = data_grad.AT(self.y)
         else:
             self.y = operand(data_grad.y, "the observation y", (1, 3))
             self.mask = operand(data_grad.mask, "the mask", (1, 3))
@@ -183,6 +188,11 @@ class _Run:
                                                int(self.mask.shape[0]), _lib.ptr(self.y), int(self.y.shape[0]),
                                                _lib.ptr(z), _lib.ptr(self.base), _lib.ptr(self.den_in), st)
                 _lib.check(rc, "psgla_img_pre_inpaint")
+            elif self.aty is not None:
+                rc = lib.psgla_img_pre_deblur_ata(C.byref(pre), self.shape, _lib.ptr(self.X), self.dg._taps_c, self.dg.l,
+                                                  _lib.ptr(self.aty), int(self.aty.shape[0]), _lib.ptr(z), _lib.ptr(self.base),
+                                                  _lib.ptr(self.den_in), st)
+                _lib.check(rc, "psgla_img_pre_deblur_ata")
             else:
                 rc = lib.psgla_img_pre_deblur(C.byref(pre), self.shape, _lib.ptr(self.X), self.dg._taps_c, self.dg.l,
                                               _lib.ptr(self.y), int(self.y.shape[0]), _lib.ptr(z), _lib.ptr(self.base),

@@ -99,6 +99,7 @@ def test_convg_argument_errors():
 
 # ----------------------------------------------------------------------------------------------------- whole network
 from oracle import image_oracle as io_  # noqa: E402
+from conftest import observed  # noqa: E402
 
 
 @pytest.fixture(scope="module")

