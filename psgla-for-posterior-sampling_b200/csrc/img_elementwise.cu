@@ -9,6 +9,7 @@
 // (the denoiser term of either update is added by the last conv layer's epilogue, csrc/conv_tc.cu).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -456,22 +457,51 @@ blur_kernel_t(PreArgs a, const Taps c_taps_arg, int B, int H, int W, const float
 // (RH + 4l) / RH.  Results differ from the two-pass-of-A formulation by fp32 rounding only (tests: 2e-5 relative).
 constexpr int ATA_THREADS = 192;
 constexpr int ATA_COLS = 256;   // strip width: 64 quads of 4 columns
-constexpr int ATA_NBUF = 4;     // cp.async ring depth (rows)
+constexpr int ATA_AHEAD = 3;    // input rows in flight beyond the one being filtered
 struct Taps2 {
   float v[4 * 4 + 1];  // k = h * h for l <= 4
 };
+template <int K2>
+struct AtaCfg {
+  static constexpr int NT = 2 * K2 + 1;            // taps of A^T A
+  static constexpr int SROW = ATA_COLS + 2 * K2;   // staged columns per channel
+  static constexpr int ROWSET = 3 * SROW;          // floats of one staged row (3 channels)
+  static constexpr int NBUF = K2 + ATA_AHEAD + 1;  // x ring: rows r - K2 (the centre of the output row) .. r + ATA_AHEAD
+  static constexpr int NABUF = ATA_AHEAD + 1;      // A^T y ring
+  static constexpr size_t SMEM = (size_t)(NBUF * ROWSET + NABUF * 3 * ATA_COLS + 2 * 3 * ATA_COLS) * sizeof(float);
+};
+
+// Phase P of the vertical window: the newest horizontally filtered row goes to slot P, the output row is the tap-weighted
+// sum of slots P + 1, P + 2, ... (mod NT) = rows r - 2 K2 .. r.  One instantiation per phase keeps the window in registers
+// with static indices; the row loop itself is NOT unrolled (an unrolled body per phase is ~5 KB of code per row step, 17 of
+// them thrash the instruction cache: 2.3 us per row step measured).
+template <int P, int NT>
+__device__ __forceinline__ void ata_vpass(float (&hring)[NT][4], const float (&o)[4], const Taps2& k, bool emit, float (&g)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hring[P][j] = o[j];
+  if (emit) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], hring[(P + 1 + t) % NT][j], acc);
+      g[j] = acc;
+    }
+  }
+}
 
 template <int K2>  // K2 = 2 l: half-width of A^T A
 __global__ void __launch_bounds__(ATA_THREADS, 2)
 deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const float* __restrict__ x,
                   const float* __restrict__ aty, int aty_B, const float* __restrict__ noise, float* __restrict__ out,
                   __nv_bfloat16* __restrict__ den_in) {
-  constexpr int NT = 2 * K2 + 1;         // taps
-  constexpr int SROW = ATA_COLS + 2 * K2;  // staged columns per channel
-  constexpr int ROWSET = 3 * SROW;       // floats of one staged row (3 channels)
+  using Cfg = AtaCfg<K2>;
+  constexpr int NT = Cfg::NT, SROW = Cfg::SROW, ROWSET = Cfg::ROWSET, NBUF = Cfg::NBUF, NABUF = Cfg::NABUF;
   constexpr int NE = (ROWSET + ATA_THREADS - 1) / ATA_THREADS;
-  __shared__ __align__(16) float ring[ATA_NBUF][ROWSET];
-  __shared__ __align__(16) float xin_s[2][3][ATA_COLS];
+  extern __shared__ __align__(16) float ata_sm[];
+  float* ring = ata_sm;                          // [NBUF][ROWSET]
+  float* aring = ring + NBUF * ROWSET;           // [NABUF][3][ATA_COLS]: every thread stages and reads its own 4 floats
+  float* xin_s = aring + NABUF * 3 * ATA_COLS;   // [2][3][ATA_COLS]
   const int tid = threadIdx.x;
   const int ch = tid >> 6, q = tid & 63;
   const int b = blockIdx.z;
@@ -480,6 +510,9 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
   const int nrows = rh + 2 * K2;         // input rows it walks
   const long long plane = (long long)H * W;
   const float* xb = x + (long long)b * 3 * plane;
+  const float* ab = aty + (long long)(aty_B > 1 ? b : 0) * 3 * plane + (long long)ch * plane;
+  const int gx0 = x0 + 4 * q;
+  const bool vec_ok = (W % 4 == 0) && gx0 + 3 < W;
   // this thread's staged elements: e = tid + 192 i  ->  (channel, staged column); global offset without the row term
   unsigned goff[NE];
 #pragma unroll
@@ -488,10 +521,11 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
     const int c = e / SROW, col = e - c * SROW;
     goff[i] = (e < ROWSET) ? (unsigned)((long long)c * plane + wrap(x0 - K2 + col, W)) : 0u;
   }
+  // One commit group per input row r: the row itself and the A^T y values of the output row it completes (r - 2 K2).
   auto stage = [&](int r) {
     if (r < nrows) {
       const long long rowoff = (long long)wrap(y0 - K2 + r, H) * W;
-      float* dst = ring[r % ATA_NBUF];
+      float* dst = ring + (r % NBUF) * ROWSET;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
         const int e = tid + ATA_THREADS * i;
@@ -500,14 +534,25 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(xb + rowoff + goff[i]) : "memory");
         }
       }
+      const int orow = r - 2 * K2;
+      if (orow >= 0 && gx0 < W) {
+        const float* src = ab + (long long)(y0 + orow) * W + gx0;
+        float* adst = aring + ((orow % NABUF) * 3 + ch) * ATA_COLS + 4 * q;
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(adst);
+        if (vec_ok) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gx0 + j < W) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr + 4 * j), "l"(src + j) : "memory");
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
-  for (int r = 0; r < ATA_NBUF - 1; ++r) stage(r);
+  for (int r = 0; r < ATA_AHEAD; ++r) stage(r);
 
-  const int gx0 = x0 + 4 * q;
-  const bool vec_ok = (W % 4 == 0) && gx0 + 3 < W;
   float hring[NT][4];  // horizontally filtered rows r - 2 K2 .. r of this thread's 4 columns
 #pragma unroll
   for (int t = 0; t < NT; ++t)
@@ -518,97 +563,91 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
   auto flush_den_in = [&](int orow) {
     if (ch == 0 && gx0 < W) {
       const int gy = y0 + orow;
-      const float(*xs)[ATA_COLS] = xin_s[orow & 1];
+      const float* xs = xin_s + (orow & 1) * 3 * ATA_COLS + 4 * q;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (gx0 + j < W)
-          store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx0 + j) * 16, xs[0][4 * q + j], xs[1][4 * q + j],
-                       xs[2][4 * q + j], a.den_in_c3);
+          store_nhwc16(den_in + ((long long)b * plane + (long long)gy * W + gx0 + j) * 16, xs[j], xs[ATA_COLS + j],
+                       xs[2 * ATA_COLS + j], a.den_in_c3);
     }
   };
 
-  for (int r0 = 0; r0 < nrows; r0 += NT) {
+  int ph = 0;
+  for (int r = 0; r < nrows; ++r) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(ATA_AHEAD - 1) : "memory");  // this thread's part of row r has landed
+    __syncthreads();           // row r is visible to all; every thread has finished iteration r - 1
+    stage(r + ATA_AHEAD);      // into the slot of row r - K2 - 1, whose last reader was iteration r - 1 (the centre row)
+    if (r > 2 * K2) flush_den_in(r - 2 * K2 - 1);  // the previous output row's xin_s is complete
+    // ---- horizontal pass on row r
+    float o[4];
+    {
+      const float4* src4 = reinterpret_cast<const float4*>(ring + (r % NBUF) * ROWSET + ch * SROW + 4 * q);
+      float in[4 + 2 * K2];
 #pragma unroll
-    for (int ph = 0; ph < NT; ++ph) {
-      const int r = r0 + ph;
-      if (r < nrows) {  // block-uniform
-        asm volatile("cp.async.wait_group %0;" ::"n"(ATA_NBUF - 2) : "memory");
-        __syncthreads();           // row r is visible; everyone is done with row r - 1 (its buffer is restaged next)
-        stage(r + ATA_NBUF - 1);
-        if (r > 2 * K2) flush_den_in(r - 2 * K2 - 1);  // the previous output row's xin_s is complete
-        // ---- horizontal pass on row r
-        {
-          const float4* src4 = reinterpret_cast<const float4*>(ring[r % ATA_NBUF] + ch * SROW + 4 * q);
-          float in[4 + 2 * K2];
+      for (int v = 0; v < (4 + 2 * K2) / 4; ++v) {
+        const float4 t = src4[v];
+        in[4 * v] = t.x, in[4 * v + 1] = t.y, in[4 * v + 2] = t.z, in[4 * v + 3] = t.w;
+      }
 #pragma unroll
-          for (int v = 0; v < (4 + 2 * K2) / 4; ++v) {
-            const float4 t = src4[v];
-            in[4 * v] = t.x, in[4 * v + 1] = t.y, in[4 * v + 2] = t.z, in[4 * v + 3] = t.w;
-          }
+      for (int j = 0; j < 4; ++j) {
+        float acc = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float acc = 0.f;
+        for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], in[j + t], acc);
+        o[j] = acc;
+      }
+    }
+    // ---- vertical pass (window in registers, one code path per phase) for output row r - 2 K2
+    const bool emit = r >= 2 * K2;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    switch (ph) {
+#define PSGLA_ATA_CASE(P_)                                        \
+  case P_:                                                        \
+    if constexpr (P_ < NT) ata_vpass<P_, NT>(hring, o, k, emit, g); \
+    break;
+      PSGLA_ATA_CASE(0) PSGLA_ATA_CASE(1) PSGLA_ATA_CASE(2) PSGLA_ATA_CASE(3) PSGLA_ATA_CASE(4) PSGLA_ATA_CASE(5)
+      PSGLA_ATA_CASE(6) PSGLA_ATA_CASE(7) PSGLA_ATA_CASE(8) PSGLA_ATA_CASE(9) PSGLA_ATA_CASE(10) PSGLA_ATA_CASE(11)
+      PSGLA_ATA_CASE(12) PSGLA_ATA_CASE(13) PSGLA_ATA_CASE(14) PSGLA_ATA_CASE(15) PSGLA_ATA_CASE(16)
+#undef PSGLA_ATA_CASE
+      default: break;
+    }
+    if (++ph == NT) ph = 0;
+    // ---- Langevin step
+    if (emit) {
+      const int orow = r - 2 * K2;
+      const int gy = y0 + orow;
+      float xin[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gx0 < W) {
+        const long long e0 = (long long)ch * plane + (long long)gy * W + gx0;  // element index inside the chain
+        const long long gi0 = (long long)b * 3 * plane + e0;
+        float xv[4], av[4], z[4];
+        const float* xc = ring + ((r - K2) % NBUF) * ROWSET + ch * SROW + K2 + 4 * q;  // the output row itself, still staged
+        const float* ac = aring + ((orow % NABUF) * 3 + ch) * ATA_COLS + 4 * q;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], in[j + t], acc);
-            hring[ph][j] = acc;
-          }
+        for (int j = 0; j < 4; ++j) xv[j] = xc[j], av[j] = ac[j];
+        if (noise) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] = (gx0 + j < W) ? noise[gi0 + j] : 0.f;
+        } else if ((e0 & 3) == 0) {
+          draw_quad(a, b, (uint32_t)e0, z);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] = draw_at(a, b, (uint32_t)(e0 + j));
         }
-        // ---- vertical pass + Langevin step for output row r - 2 K2
-        if (r >= 2 * K2) {
-          const int orow = r - 2 * K2;
-          const int gy = y0 + orow;
-          float g[4];
+        float bv[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float acc = 0.f;
+        for (int j = 0; j < 4; ++j) {
+          bv[j] = langevin_base(a, xv[j], g[j] - av[j], z[j]);
+          xin[j] = (a.alg == PSGLA_ALG_PNPULA) ? xv[j] : bv[j];
+        }
+        if (vec_ok) {
+          *reinterpret_cast<float4*>(out + gi0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        } else {
 #pragma unroll
-            for (int t = 0; t < NT; ++t) acc = fmaf(k.v[t], hring[(ph + 1 + t) % NT][j], acc);  // rows r - 2 K2 + t
-            g[j] = acc;
-          }
-          float xin[4] = {0.f, 0.f, 0.f, 0.f};
-          if (gx0 < W) {
-            const long long e0 = (long long)ch * plane + (long long)gy * W + gx0;  // element index inside the chain
-            const long long gi0 = (long long)b * 3 * plane + e0;
-            const long long ai0 = (long long)(aty_B > 1 ? b : 0) * 3 * plane + e0;
-            float xv[4], av[4], z[4];
-            if (vec_ok) {
-              const float4 t0 = *reinterpret_cast<const float4*>(x + gi0);
-              const float4 t1 = *reinterpret_cast<const float4*>(aty + ai0);
-              xv[0] = t0.x, xv[1] = t0.y, xv[2] = t0.z, xv[3] = t0.w;
-              av[0] = t1.x, av[1] = t1.y, av[2] = t1.z, av[3] = t1.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                xv[j] = (gx0 + j < W) ? x[gi0 + j] : 0.f;
-                av[j] = (gx0 + j < W) ? aty[ai0 + j] : 0.f;
-              }
-            }
-            if (noise) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) z[j] = (gx0 + j < W) ? noise[gi0 + j] : 0.f;
-            } else if ((e0 & 3) == 0) {
-              draw_quad(a, b, (uint32_t)e0, z);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) z[j] = draw_at(a, b, (uint32_t)(e0 + j));
-            }
-            float bv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              bv[j] = langevin_base(a, xv[j], g[j] - av[j], z[j]);
-              xin[j] = (a.alg == PSGLA_ALG_PNPULA) ? xv[j] : bv[j];
-            }
-            if (vec_ok) {
-              *reinterpret_cast<float4*>(out + gi0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (gx0 + j < W) out[gi0 + j] = bv[j];
-            }
-          }
-          *reinterpret_cast<float4*>(&xin_s[orow & 1][ch][4 * q]) = make_float4(xin[0], xin[1], xin[2], xin[3]);
+          for (int j = 0; j < 4; ++j)
+            if (gx0 + j < W) out[gi0 + j] = bv[j];
         }
       }
+      *reinterpret_cast<float4*>(xin_s + ((orow & 1) * 3 + ch) * ATA_COLS + 4 * q) = make_float4(xin[0], xin[1], xin[2], xin[3]);
     }
   }
   __syncthreads();
@@ -792,8 +831,10 @@ static void ata_taps(const float* h, int l, Taps2* k) {
 template <int K2>
 static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const float* x, const float* aty, int aty_B,
                       const float* noise, float* out, void* den_in, cudaStream_t st) {
-  // rows per block: the busiest SM holds ceil(blocks / SMs) blocks of RH + 2 K2 row steps each
-  const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = num_sms();
+  // rows per block: two blocks are resident per SM (registers) and hide each other's latencies, so the launch takes about
+  // ceil(blocks / (2 SMs)) rounds of RH + 2 K2 row steps (measured at 32 chains of 256 x 256, l = 4: RH = 8 / 16 / 32 / 64 / 128
+  // -> 87 / 71 / 64 / 87 / 163 us; the four-pass kernel 83 us)
+  const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = 2 * num_sms();
   int best_rh = 16;
   long long best = -1;
   for (int rh = 8; rh <= 128; rh *= 2) {
@@ -801,8 +842,19 @@ static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const
     const long long cost = ((blocks + sms - 1) / sms) * (rh + 2 * K2);
     if (best < 0 || cost < best) best = cost, best_rh = rh;
   }
+  if (const char* e = std::getenv("PSGLA_ATA_RH")) {  // A/B runs
+    const int v = std::atoi(e);
+    if (v >= 1) best_rh = v;
+  }
   PSGLA_REQUIRE(s.B <= 65535 && (s.H + best_rh - 1) / best_rh <= 65535, "too many chains / rows for one launch");
-  deblur_ata_kernel<K2><<<dim3(strips, (s.H + best_rh - 1) / best_rh, s.B), ATA_THREADS, 0, st>>>(
+  constexpr size_t smem = AtaCfg<K2>::SMEM;
+  static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
+  const unsigned long long dev_bit = 1ull << (current_device() & 63);
+  if (smem > 48 * 1024 && !(attr_done.load(std::memory_order_acquire) & dev_bit)) {
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(deblur_ata_kernel<K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
+  }
+  deblur_ata_kernel<K2><<<dim3(strips, (s.H + best_rh - 1) / best_rh, s.B), ATA_THREADS, smem, st>>>(
       a, k, s.B, s.H, s.W, best_rh, x, aty, aty_B, noise, out, (__nv_bfloat16*)den_in);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
