@@ -1592,17 +1592,15 @@ static int launch_hidden_chain(void* buf0, void* buf1, int n_layers, const uint8
 }
 
 // Measured on B200 (1-16 chains of 256 x 256): the chain is NOT faster than the per-layer launches (181.7 vs 187.8 us per
-// DnCNN application at one chain).  A layer's ~8 us at that size is pipeline fill and drain inside the CTA -- TMA load
+// DnCNN application at one chain in round 1; 174.6 vs 176.9 us in round 2, and 8-20 % SLOWER at 4-16 chains).  Round 2 also
+// tried replacing the grid barrier by per-item flags (an item waits only for the <= 9 items whose rows / halo pixels it
+// reads): 224 us -- the acquire-polls of the neighbours' flags cost more than the barrier's single counter.  A layer's ~8 us at that size is pipeline fill and drain inside the CTA -- TMA load
 // latency, three rows through the loader warps before the first MMA, the last row's epilogue and store -- not launch
 // overhead, which PDL already overlaps; the grid barrier costs what the kernel boundary cost.  The kernel stays as a
 // tested alternative (PSGLA_CHAIN=1) and as the base for keeping a CTA's own rows on chip between layers.
 static bool use_chain(const ConvParams&) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* e = getenv("PSGLA_CHAIN");
-    forced = e ? atoi(e) : 0;
-  }
-  return conv_use_ts() && forced == 1;
+  const char* e = getenv("PSGLA_CHAIN");  // read per call: tests and A/B scripts switch it inside one process
+  return conv_use_ts() && e && atoi(e) == 1;
 }
 
 // ---- packed weight layout: per layer [weights (9 taps, swizzled) | bias fp32], each layer 1024 B aligned
@@ -1666,8 +1664,8 @@ extern "C" int psgla_dncnn_pack_weights(int depth, const float* const* weights_h
 }
 
 extern "C" size_t psgla_dncnn_workspace_bytes(psgla_img_shape s) {
-  // two ping-pong activation buffers (each rounded up to 1 KB) + 1 KB holding the layer-chain kernel's grid barrier
-  return 2 * (((size_t)s.B * s.H * s.W * 64 * 2 + 1023) / 1024 * 1024) + 1024 + 1024;
+  // two ping-pong activation buffers (each rounded up to 1 KB) + 4 KB holding the layer-chain kernel's barrier / item flags
+  return 2 * (((size_t)s.B * s.H * s.W * 64 * 2 + 1023) / 1024 * 1024) + 4096 + 1024;
 }
 
 static int check_shape(const psgla_img_shape& s) {

@@ -281,10 +281,19 @@ class DRUNet:
         _lib.check(rc, "psgla_drunet_denoise_post_next")
 
     def forward(self, x, sigma):
+        """D(x; sigma), fp32 [B,3,H,W] in and out.  The U-Net halves the resolution three times, so H and W must be multiples
+        of 8; other sizes (CBSD68's 481 x 321) are replication-padded at the bottom / right to the next multiple, denoised and
+        cropped -- KAIR's ``test_pad`` rule, which is what deepinv applies to small inputs (its rule for large ones, a 4-way
+        overlapping split, cannot be verified offline: a documented deviation).  The fused sampler path (``apply_post``) does
+        not pad: crop or pad the PROBLEM for psgla / pnpula (e.g. 481 x 321 -> 480 x 320)."""
         if not x.is_cuda:
             raise RuntimeError("DRUNet.forward needs a CUDA tensor: there is no CPU path")
         sigma = float(sigma.reshape(-1)[0]) if isinstance(sigma, torch.Tensor) else float(sigma)
         x = x.to(torch.float32).contiguous()
+        H0, W0 = int(x.shape[2]), int(x.shape[3])
+        ph, pw = (-H0) % 8, (-W0) % 8
+        if ph or pw:
+            x = torch.nn.functional.pad(x, (0, pw, 0, ph), mode="replicate").contiguous()
         shape = _lib.ImgShape(int(x.shape[0]), 3, int(x.shape[2]), int(x.shape[3]))
         _, den_in = self.buffers(shape)
         out = torch.empty_like(x)
@@ -292,6 +301,6 @@ class DRUNet:
             _lib.check(_lib.lib().psgla_img_to_nhwc16(shape, _lib.ptr(x), sigma, _lib.ptr(den_in), _lib.stream_ptr(self.device)),
                        "psgla_img_to_nhwc16")
         self.apply_post(shape, den_in, x, _lib.PostParams(1.0, 0.0, 0.0, 1.0), out)  # out = 0 * x + 1 * D(x)
-        return out
+        return out[:, :, :H0, :W0].contiguous() if (ph or pw) else out
 
     __call__ = forward

@@ -129,19 +129,36 @@ def sample_posterior(A, y, sigma, N, mu_list, sigma_list, pi_list, rng=None):
     return sample_gaussian(*constantes_conditionnal_prob(A, y, sigma, mu_list, sigma_list, pi_list), N, rng=rng)
 
 
+def _uniform_transport_cost(M):
+    """min <T, M> over T >= 0 with row sums 1/n1 and column sums 1/n2: the transport LP ``ot.emd2(a=[], b=[], M)`` solves for
+    clouds of UNEQUAL size (n1 n2 variables, n1 + n2 equalities; HiGHS through scipy)."""
+    from scipy.optimize import linprog
+    from scipy.sparse import coo_matrix
+    n1, n2 = M.shape
+    rows = np.concatenate([np.repeat(np.arange(n1), n2), n1 + np.tile(np.arange(n2), n1)])
+    cols = np.concatenate([np.arange(n1 * n2), np.arange(n1 * n2)])
+    A = coo_matrix((np.ones(2 * n1 * n2), (rows, cols)), shape=(n1 + n2, n1 * n2)).tocsr()
+    b = np.concatenate([np.full(n1, 1.0 / n1), np.full(n2, 1.0 / n2)])
+    res = linprog(M.reshape(-1), A_eq=A[:-1], b_eq=b[:-1], bounds=(0, None), method="highs")  # one equality is redundant
+    if res.status != 0:
+        raise RuntimeError("transport LP did not converge: %s" % res.message)
+    return float(res.fun)
+
+
 def Wasserstein_distance(sample1, sample2, n_sub=1000, rng=None):
     """Exact optimal transport between random ``n_sub``-point subsamples with squared-Euclidean cost, i.e. W2^2
-    (utils_2D.py:235-244: ``ot.dist`` default metric + ``ot.emd2`` with uniform weights).  POT is replaced by the
-    assignment problem, which is the same linear programme for equal-size uniform clouds."""
+    (utils_2D.py:235-244: ``ot.dist`` default metric + ``ot.emd2`` with uniform weights).  POT is replaced by the assignment
+    problem -- the same linear programme for equal-size uniform clouds -- and, for clouds of unequal size (``sample_posterior``
+    returns sum_i int(pi_i N) points, e.g. 99 against a 100-point chain), by the uniform-marginal transport LP itself."""
     from scipy.optimize import linear_sum_assignment
     perm = np.random.permutation if rng is None else rng.permutation
     s1 = perm(np.asarray(sample1))[:n_sub]
     s2 = perm(np.asarray(sample2))[:n_sub]
-    n = min(len(s1), len(s2))
-    s1, s2 = s1[:n], s2[:n]
     M = ((s1[:, None, :] - s2[None, :, :]) ** 2).sum(-1)
+    if len(s1) != len(s2):
+        return _uniform_transport_cost(M)
     rows, cols = linear_sum_assignment(M)
-    return float(M[rows, cols].sum() / n)
+    return float(M[rows, cols].sum() / len(s1))
 
 
 def sliced_wasserstein_distance(X, Y, n_projections=50, seed=None):

@@ -136,10 +136,19 @@ def test_drunet_forward_against_fp32_oracle(drunets, B, H, W):
     assert (got - ref).abs().max().item() < 5e-2 * max(1.0, ref.abs().max().item())
 
 
-def test_drunet_rejects_sizes_not_multiple_of_8(drunets):
-    den, _ = drunets
+def test_drunet_sizes_not_multiple_of_8(drunets):
+    """forward() pads by replication to the next multiple of 8 and crops (KAIR test_pad); the fused sampler path refuses."""
+    den, net = drunets
+    x = torch.rand(1, 3, 36, 61, device="cuda")
+    got = den.forward(x, 0.02)
+    xp = F.pad(x, (0, 3, 0, 4), mode="replicate")
+    with torch.no_grad():
+        want = net(xp, 0.02)[:, :, :36, :61]
+    assert got.shape == x.shape
+    assert ((got - want).norm() / want.norm()).item() < 3e-2
+    dg, init, _, _ = P.make_inpainting(x)
     with pytest.raises(RuntimeError, match="multiples of 8"):
-        den.forward(torch.rand(1, 3, 36, 64, device="cuda"), 0.02)
+        P.psgla(init, dg, den, 1.0, 25.0, 5 / 255, (5 / 255) ** 2, n_iter=2, n_inter=1, n_inter_mmse=1, seed=0)
 
 
 def test_psgla_drunet_replay_against_oracle(drunets):

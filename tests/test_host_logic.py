@@ -155,3 +155,19 @@ def test_sliced_wasserstein_is_exact_for_translations_and_permutation_invariant(
     want = np.sqrt(np.mean((t @ th) ** 2))
     assert abs(got - want) < 1e-12
     assert abs(P.sliced_wasserstein_distance(X[rng.permutation(500)], Y[rng.permutation(500)], 64, seed=5) - got) < 1e-12
+
+
+def test_wasserstein_unequal_sizes_solves_the_transport_lp():
+    """ot.emd2 with uniform weights is the transport LP for any pair of sizes (utils_2D.py:242-243); sample_posterior returns
+    sum_i int(pi_i N) points, so 99-against-100 clouds do occur.  Equal sizes: the LP equals the assignment problem; unequal:
+    a hand-checked 2-against-3 instance and consistency with the equal-size value when one point is dropped."""
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=(60, 2)), rng.normal(size=(60, 2)) + 0.5
+    M = ((a[:, None] - b[None]) ** 2).sum(-1)
+    eq = P.Wasserstein_distance(a, b, rng=np.random.default_rng(1))
+    assert abs(P.utils_2D._uniform_transport_cost(M) - eq) < 1e-9
+    x = np.array([[0.0, 0.0], [1.0, 0.0]])
+    y = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    assert abs(P.Wasserstein_distance(x, y, rng=np.random.default_rng(0)) - 0.5) < 1e-9  # 1/6 and 1/3 of the mass move one unit
+    un = P.Wasserstein_distance(a[:59], b, rng=np.random.default_rng(1))
+    assert abs(un - eq) < 0.1 * eq
