@@ -621,3 +621,29 @@ def test_second_device_after_first():
         fin, _ = P.run_chains("psgla", 50, np.zeros(2), 0.3, np.eye(2), 1, D, 2 / 3, n_chains=4096, seed=0, device=dev)
         outs.append(fin.cpu())
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+def test_run_image_set_equals_per_image_runs(nets):
+    """psgla_b200.run_image_set (one process = world size 1 here; the dealing / gathering logic at world sizes 2 and 3 is
+    tests/test_dist_gloo.py): three images of different sizes, 2 chains each, statistics-only mode.  Every row must equal what a
+    direct psgla() call on that image with chain_id0 = index * n_chains gives -- the invariant that makes the result independent
+    of how many GPUs share the set."""
+    den, _ = nets
+    g = torch.Generator().manual_seed(3)
+    images = [torch.rand(3, 32, 40, generator=g), torch.rand(3, 24, 24, generator=g), torch.rand(1, 3, 40, 32, generator=g)]
+    prm = dict(P.sampler_params("psgla", den="DnCNN", N=1000), N=14, n_inter=2, n_inter_mmse=2)
+    res = P.run_image_set(images, den, problem="inpainting", alg="psgla", n_chains=2, params=prm, seed=5, keep_maps=True)
+    assert [d["index"] for d in res] == [0, 1, 2] and all(d["n_chains"] == 2 and d["n_windows"] == 14 // 3 for d in res)
+    for i, im in enumerate(images):
+        imc = im.reshape(1, 3, im.shape[-2], im.shape[-1]).cuda()
+        dg, init, y, _ = P.make_inpainting(imc, prop=0.5, sigma=1.0, seed_ip=0)
+        X, M, M2 = P.psgla(init, dg, den, **P.as_psgla_kwargs(prm, seed=5), n_chains=2, chain_id0=2 * i, rng="philox")
+        xmmse = torch.stack(M).mean(0).mean(0)  # mean over windows, then over the two chains
+        assert (res[i]["xmmse"] - xmmse).abs().max().item() < 1e-6
+        p, s = P.psnr_ssim(xmmse, imc[0])
+        assert abs(res[i]["psnr_mmse"] - p.item()) < 1e-3 and abs(res[i]["ssim_mmse"] - s.item()) < 1e-4
+        assert (res[i]["H"], res[i]["W"]) == (im.shape[-2], im.shape[-1])
+    # deblurring + PnP-ULA through the same entry
+    prm_u = dict(P.sampler_params("pnp_ula", den="DnCNN", N=1000), N=9, n_inter=2, n_inter_mmse=2)
+    res_u = P.run_image_set(images[:1], den, problem="deblurring", alg="pnp_ula", n_chains=3, params=prm_u, seed=1)
+    assert len(res_u) == 1 and res_u[0]["n_chains"] == 3 and np.isfinite(res_u[0]["psnr_mmse"])
