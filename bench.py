@@ -211,6 +211,32 @@ def measure_fp32_peak(P, torch, dev):
     return best
 
 
+# FP32 pipe slots per chain-step of gmm2d_lean_kernel<ALG, STRUCT, 4, 64, 16, 1> (SASS of the loop, scalar FP32 + 2 x packed):
+# the NF of the matching instruction-mix probe (psgla_selftest_pipe_rate mode 100 + NF)
+MIX_NF = {("psgla", 2): 21, ("pnp_ula", 2): 23, ("psgla", 1): 26, ("pnp_ula", 1): 28, ("psgla", 0): 28, ("pnp_ula", 0): 30}
+
+
+def measure_mix_ceiling(P, torch, dev):
+    """Chain-steps/s this GPU sustains for the chain kernel's per-step INSTRUCTION MIX (6 MUFU, 9 IMAD.WIDE.U32, NF FP32, 10 LOP3,
+    2 I2FP) when the instructions are independent (csrc/selftest.cu, pipe_rate_kernel<11, NF>): the measured roofline of a kernel
+    that is bound by neither memory nor a single pipe but by how the SM issues this mix.  One figure per NF."""
+    lib = P._lib.lib()
+    scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=dev)
+    out = {}
+    for nf in sorted(set(MIX_NF.values())):
+        ops = C.c_double()
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            P._lib.check(lib.psgla_selftest_pipe_rate(100 + nf, 20000, 8, scratch.data_ptr(), C.byref(ops), P._lib.stream_ptr(dev)), "pipe_rate")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+        out[nf] = best
+    return out
+
+
 def gmm_structure(P, prior):
     """Which specialisation of the chain kernel a cell takes (csrc/gmm2d.cu constants_structure): 2 = all matrices diagonal
     (isotropic / axis-aligned covariances), 1 = only the data term (A = I), 0 = general."""
@@ -387,7 +413,8 @@ def bench_gmm2d(args, P, torch, rank, ws, dev):
             w2["%s|%s|y=(%g,%g)" % (alg, prior, y[0], y[1])] = round(P.Wasserstein_distance(sub, ref, rng=rng), 4)
     units = float(n_chains) * n_steps * K * ws
     pipe_cycles = sum(FMA_PIPE_CYCLES_PER_WARP_STEP[gmm_structure(P, CELLS[k % len(CELLS)][0])] for k in range(W, W + K)) / K
-    return dict(pipe_cycles=pipe_cycles, value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
+    cells_nf = [MIX_NF[(CELLS[k % len(CELLS)][2], gmm_structure(P, CELLS[k % len(CELLS)][0]))] for k in range(W, W + K)]
+    return dict(cells_nf=cells_nf, pipe_cycles=pipe_cycles, value=units / (total_ms * 1e-3), total_ms=total_ms, per_step_ms=per_step, flop=flop,
                 e2e_value=units / (e2e_ms * 1e-3), e2e_ms=e2e_ms, h2d=n_chains * 2 * 4, d2h=n_chains * 2 * 4, w2=w2,
                 launches_per_step=launches_per_step)
 
@@ -990,6 +1017,7 @@ def main():
         args.warmup = W
 
     fp32_peak = measure_fp32_peak(P, torch, dev)
+    mix = measure_mix_ceiling(P, torch, dev)
     sampler = ClockSampler(local)  # clocks during the headline (2D) timed regions ...
     if rank == 0:
         sampler.start()
@@ -1041,10 +1069,19 @@ def main():
                                   "cycles_taken_per_warp_step": (clocks or {}).get("sm_mhz") and
                                   (clocks["sm_mhz"] * 1e6 * 148 * 4 * 32) / (g["value"] / ws),
                                   "note": "taken = sm_clock x 592 SM sub-partitions x 32 lanes / (chain-steps/s); needed / taken = FMA-pipe utilisation"},
+                     # the bound that binds: the issue ceiling of the kernel's own instruction mix, measured by a dependency-free probe
+                     # of the same mix on this GPU; a timed step = one cell, so the ceiling of the run is the harmonic mean over its cells
+                     "instruction_mix": {"ceiling": len(g["cells_nf"]) / sum(1.0 / mix[nf] for nf in g["cells_nf"]),
+                                         "unit": "chain-steps/s per GPU",
+                                         "frac": (g["value"] / ws) / (len(g["cells_nf"]) / sum(1.0 / mix[nf] for nf in g["cells_nf"])),
+                                         "per_fp32_count": {str(k): v for k, v in mix.items()},
+                                         "note": "6 MUFU + 9 IMAD.WIDE.U32 + NF FP32 + 10 LOP3 + 2 I2FP per chain-step as independent chains "
+                                                 "(psgla_selftest_pipe_rate 100 + NF), NF = 21 / 23 (diagonal cells, PSGLA / PnP-ULA), 26 / 28 (cross prior)"},
                      "launch_ms": g["total_ms"] / K / g["launches_per_step"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_gmm2d_lean_full.txt)
-                     "traffic": None,
-                     "traffic_source": "profiles/r02_gmm2d_lean_full.txt"},
+                     "traffic": 8.03e6 if args.chains == 1000000 else None,
+                     "traffic_source": "profiles/r02_gmm2d_lean_full.txt (8.06 / 8.01 MB read, 0 written back to DRAM within the launch: "
+                                       "8 B per chain in, the 8 B per chain out stay in L2)"},
         "w2_squared_to_true_posterior": g["w2"],
     }
     if strong is not None:

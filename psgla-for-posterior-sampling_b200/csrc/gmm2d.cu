@@ -446,10 +446,15 @@ static int constants_structure(const Gmm2dConsts<float>& c) {
 // 64-bit bookkeeping of the optional replay / trajectory paths).  One chain per thread; each round draws NB counter blocks
 // (2 NB steps), with the Box-Muller arithmetic of two blocks packed into FFMA2 / FMUL2 when PK.  Same Philox counters, same
 // arithmetic per chain as gmm2d_kernel: bit-identical results.
-template <int ALG, int STRUCT, int NB, int BLOCK, int MINB, bool PK>
+// MODE bit 0: Box-Muller arithmetic of two counter blocks packed (FFMA2 / FMUL2); bit 1: software pipelining -- the Philox
+// words of round r + 1 are computed in the same loop body as the Box-Muller transform and the Langevin steps of round r, so
+// that every warp offers the scheduler IMAD.WIDE (FMA pipe), MUFU (XU pipe) and FFMA work at the same time instead of in
+// three phases.
+template <int ALG, int STRUCT, int NB, int BLOCK, int MINB, int MODE>
 __global__ void __launch_bounds__(BLOCK, MINB)
 gmm2d_lean_kernel(const Gmm2dConsts<float> c, float2* __restrict__ x, unsigned n_launch, unsigned long long sub0,
                   unsigned long long pair0, int n_rounds, const PhiloxKeys keys) {
+  constexpr bool PK = (MODE & 1) != 0 && NB % 2 == 0, PIPE = (MODE & 2) != 0;
   const unsigned g = blockIdx.x * BLOCK + threadIdx.x;
   if (g >= n_launch) return;
   float2 v = x[g];
@@ -457,19 +462,21 @@ gmm2d_lean_kernel(const Gmm2dConsts<float> c, float2* __restrict__ x, unsigned n
   const unsigned long long sub = sub0 + g;
   const uint32_t s_lo = (uint32_t)sub, s_hi = (uint32_t)(sub >> 32);
   unsigned long long pair = pair0;
-  for (int r = 0; r < n_rounds; ++r, pair += NB) {
-    float z[NB][4];
-    if constexpr (PK && NB % 2 == 0) {
+  auto words = [&](unsigned long long pr0, uint32_t (&w)[NB][4]) {  // Philox4x32-10 of counter blocks pr0 .. pr0 + NB - 1
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const unsigned long long pr = pr0 + b;
+      w[b][0] = (uint32_t)pr, w[b][1] = (uint32_t)(pr >> 32), w[b][2] = s_lo, w[b][3] = s_hi;
+      philox4x32_10_keyed(w[b][0], w[b][1], w[b][2], w[b][3], keys);
+    }
+  };
+  auto normals = [&](const uint32_t (&w)[NB][4], float (&z)[NB][4]) {
+    if constexpr (PK) {
 #pragma unroll
       for (int b = 0; b < NB; b += 2) {
-        const unsigned long long pa = pair + b, pb = pair + b + 1;
-        uint32_t a0 = (uint32_t)pa, a1 = (uint32_t)(pa >> 32), a2 = s_lo, a3 = s_hi;
-        uint32_t b0 = (uint32_t)pb, b1 = (uint32_t)(pb >> 32), b2 = s_lo, b3 = s_hi;
-        philox4x32_10_keyed(a0, a1, a2, a3, keys);
-        philox4x32_10_keyed(b0, b1, b2, b3, keys);
         pk2 q0, q1, q2, q3;
-        box_muller_pk(a0, a1, b0, b1, q0, q1);
-        box_muller_pk(a2, a3, b2, b3, q2, q3);
+        box_muller_pk(w[b][0], w[b][1], w[b + 1][0], w[b + 1][1], q0, q1);
+        box_muller_pk(w[b][2], w[b][3], w[b + 1][2], w[b + 1][3], q2, q3);
         unpk(q0, z[b][0], z[b + 1][0]);
         unpk(q1, z[b][1], z[b + 1][1]);
         unpk(q2, z[b][2], z[b + 1][2]);
@@ -478,14 +485,36 @@ gmm2d_lean_kernel(const Gmm2dConsts<float> c, float2* __restrict__ x, unsigned n
     } else {
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        const unsigned long long pr = pair + b;
-        philox_normal4_keyed(keys, sub, (uint32_t)pr, (uint32_t)(pr >> 32), z[b][0], z[b][1], z[b][2], z[b][3]);
+        box_muller(w[b][0], w[b][1], z[b][0], z[b][1]);
+        box_muller(w[b][2], w[b][3], z[b][2], z[b][3]);
       }
     }
+  };
+  uint32_t w[NB][4];
+  if (PIPE) words(pair, w);
+  for (int r = 0; r < n_rounds; ++r, pair += NB) {
+    float z[NB][4];
+    if (PIPE) {
+      uint32_t wn[NB][4];
+      words(pair + NB, wn);  // one round ahead (the last iteration's are unused)
+      normals(w, z);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][0], z[b][1]);
-      langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][2], z[b][3]);
+      for (int b = 0; b < NB; ++b) {
+        langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][0], z[b][1]);
+        langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][2], z[b][3]);
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[b][i] = wn[b][i];
+    } else {
+      words(pair, w);
+      normals(w, z);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][0], z[b][1]);
+        langevin_step_s<ALG, STRUCT>(c, x0, x1, z[b][2], z[b][3]);
+      }
     }
   }
   x[g] = float2{x0, x1};
@@ -758,7 +787,7 @@ static int launch_lean_s(int nb, int block, int minb, int pk, const Launch& a, l
   const unsigned long long sub0 = a.chain_id0 + (unsigned long long)lo, pair0 = (unsigned long long)step_lo >> 1;
 #define PSGLA_LEAN(N_, B_, M_, P_)                                                                                          \
   if (nb == N_ && block == B_ && minb == M_ && pk == P_) {                                                                  \
-    gmm2d_lean_kernel<ALG, STRUCT, N_, B_, M_, (P_ != 0)><<<(unsigned)((n + B_ - 1) / B_), B_, 0, a.st>>>(                    \
+    gmm2d_lean_kernel<ALG, STRUCT, N_, B_, M_, P_><<<(unsigned)((n + B_ - 1) / B_), B_, 0, a.st>>>(                           \
         c, x, (unsigned)n, sub0, pair0, (int)n_rounds, a.keys);                                                             \
     return PSGLA_OK;                                                                                                        \
   }
@@ -769,6 +798,16 @@ static int launch_lean_s(int nb, int block, int minb, int pk, const Launch& a, l
   PSGLA_LEAN(4, 64, 24, 0)
   PSGLA_LEAN(4, 32, 32, 1)
   PSGLA_LEAN(8, 32, 32, 0)
+  PSGLA_LEAN(1, 64, 16, 2)
+  PSGLA_LEAN(2, 64, 16, 2)
+  PSGLA_LEAN(2, 64, 16, 3)
+  PSGLA_LEAN(4, 64, 16, 2)
+  PSGLA_LEAN(4, 64, 16, 3)
+  PSGLA_LEAN(1, 64, 24, 2)
+  PSGLA_LEAN(2, 64, 24, 2)
+  PSGLA_LEAN(2, 64, 20, 3)
+  PSGLA_LEAN(4, 64, 12, 3)
+  PSGLA_LEAN(4, 64, 12, 2)
 #undef PSGLA_LEAN
   return set_error(PSGLA_E_UNSUPPORTED, "lean gmm2d geometry nb=%d block=%d minb=%d pk=%d is not instantiated", nb, block, minb, pk);
 }

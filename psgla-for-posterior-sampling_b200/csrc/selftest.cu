@@ -53,7 +53,12 @@ __global__ void __launch_bounds__(256) fp32_rate_kernel(int iters, float seed, f
 // every thread runs iters x 32 instructions of ONE class in 8 independent dependency chains.
 //   0 IMAD.WIDE.U32 (mul.wide.u32, the Philox round multiply)   1 IMAD.HI.U32 (mul.hi.u32)   2 IMAD (mul.lo.u32)
 //   3 LOP3 (3-input xor)   4 MUFU.EX2   5 I2FP.F32.U32   6 FFMA   7 MUFU.SIN   8 IMAD.WIDE + FFMA interleaved 1:1
-template <int MODE>
+//   9 MUFU.EX2 + IMAD.WIDE 1:1   10 MUFU.EX2 + 4 FFMA
+//   11 / 100 + NF: the chain kernel's per-step MIX as independent chains (6 MUFU, 9 IMAD.WIDE, NF FFMA, 10 LOP3, 2 I2FP per
+//      "step", 4 steps per loop round; NF = 19 for mode 11, else 21 / 23 / 26 / 28 / 30 = the FP32 pipe slots per step of the six
+//      (algorithm, constants-structure) specialisations of gmm2d_lean_kernel): what the SM sustains for this instruction mix
+//      when no instruction waits for another -- the measured ceiling the chain kernel is held against
+template <int MODE, int NF = 19>
 __global__ void __launch_bounds__(256) pipe_rate_kernel(int iters, unsigned seed, unsigned* __restrict__ out) {
   unsigned v[8];
   float f[8];
@@ -88,13 +93,52 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(int iters, unsigned seed
           f[j] = fmaf(f[j], a, b);
         } else if (MODE == 7) {
           asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
-        } else {
+        } else if (MODE == 8) {
           unsigned long long p;
           asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(v[j]), "r"(m));
           v[j] = (unsigned)(p >> 32) ^ (unsigned)p;
           f[j] = fmaf(f[j], a, b);
+        } else if (MODE == 9) {
+          unsigned long long p;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(v[j]), "r"(m));
+          v[j] = (unsigned)(p >> 32) ^ (unsigned)p;
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
+        } else if (MODE == 10) {
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
+          float g = f[(j + 1) & 7];
+          g = fmaf(g, a, b), g = fmaf(g, a, b), g = fmaf(g, a, b), g = fmaf(g, a, b);
+          f[(j + 1) & 7] = g;
         }
       }
+    if (MODE == 11) {
+      float e[6];  // MUFU chains
+      unsigned w[3];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) e[q] = f[q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) w[q] = v[q];
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {  // 4 "steps"
+#pragma unroll
+        for (int q = 0; q < 6; ++q) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e[q]));
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          unsigned long long p;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(w[q % 3]), "r"(m));
+          asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(w[q % 3]) : "r"((unsigned)(p >> 32)), "r"((unsigned)p), "r"(m));
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[6 + (q & 1)]) : "f"(a), "f"(b));
+        float c0, c1;
+        asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(c0) : "r"(w[0]));
+        asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(c1) : "r"(w[1]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[7]) : "r"(__float_as_uint(c0)), "r"(__float_as_uint(c1)));  // the 10th LOP3
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) f[q] = e[q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) v[q] = w[q];
+    }
   }
   unsigned s = 0;
 #pragma unroll
@@ -121,7 +165,7 @@ extern "C" int psgla_selftest_fp32_rate(int mode, int iters, int blocks_per_sm, 
 }
 
 extern "C" int psgla_selftest_pipe_rate(int mode, int iters, int blocks_per_sm, void* out_dev, double* ops_out, void* stream) {
-  PSGLA_REQUIRE(mode >= 0 && mode <= 8 && iters > 0 && blocks_per_sm > 0 && blocks_per_sm <= 8 && out_dev != nullptr,
+  PSGLA_REQUIRE(((mode >= 0 && mode <= 11) || mode == 121 || mode == 123 || mode == 126 || mode == 128 || mode == 130) && iters > 0 && blocks_per_sm > 0 && blocks_per_sm <= 8 && out_dev != nullptr,
                 "psgla_selftest_pipe_rate: bad argument");
   const int grid = num_sms() * blocks_per_sm;
   cudaStream_t st = (cudaStream_t)stream;
@@ -135,9 +179,18 @@ extern "C" int psgla_selftest_pipe_rate(int mode, int iters, int blocks_per_sm, 
     case 5: pipe_rate_kernel<5><<<grid, 256, 0, st>>>(iters, 3u, o); break;
     case 6: pipe_rate_kernel<6><<<grid, 256, 0, st>>>(iters, 3u, o); break;
     case 7: pipe_rate_kernel<7><<<grid, 256, 0, st>>>(iters, 3u, o); break;
-    default: pipe_rate_kernel<8><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 8: pipe_rate_kernel<8><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 9: pipe_rate_kernel<9><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 10: pipe_rate_kernel<10><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 121: pipe_rate_kernel<11, 21><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 123: pipe_rate_kernel<11, 23><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 126: pipe_rate_kernel<11, 26><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 128: pipe_rate_kernel<11, 28><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    case 130: pipe_rate_kernel<11, 30><<<grid, 256, 0, st>>>(iters, 3u, o); break;
+    default: pipe_rate_kernel<11><<<grid, 256, 0, st>>>(iters, 3u, o); break;
   }
   PSGLA_CUDA_TRY(cudaGetLastError());
-  if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * 32.0;  // thread-level instructions of the probed class
+  // thread-level instructions of the probed class; mode 11: thread-level "steps" (4 per loop round)
+  if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * (mode >= 11 ? 4.0 : 32.0);
   return PSGLA_OK;
 }

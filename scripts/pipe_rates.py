@@ -10,7 +10,7 @@ import torch  # noqa: E402
 import psgla_b200 as P  # noqa: E402
 
 NAMES = ["IMAD.WIDE.U32", "IMAD.HI.U32", "IMAD (lo)", "LOP3", "MUFU.EX2", "I2FP.F32.U32", "FFMA", "MUFU.SIN (+FMUL.RZ)",
-         "IMAD.WIDE + FFMA 1:1"]
+         "IMAD.WIDE + FFMA 1:1", "MUFU.EX2 + IMAD.WIDE 1:1", "MUFU.EX2 + 4 FFMA", "chain-step mix (6M 9W 19F 10L 2C)"]
 lib = P._lib.lib()
 scratch = torch.empty(148 * 8 * 256, dtype=torch.float32, device="cuda")
 sms = torch.cuda.get_device_properties(0).multi_processor_count
@@ -26,4 +26,7 @@ for mode, name in enumerate(NAMES):
         t = e0.elapsed_time(e1) * 1e-3
         best = t if best is None else min(best, t)
     per_s = ops.value / best
-    print("%-24s %8.2f Gop/s/SM  = %6.2f thread-instr/clk/SM at 1.9 GHz" % (name, per_s / sms / 1e9, per_s / sms / 1.9e9), flush=True)
+    clk = torch.cuda.clock_rate() * 1e6 if hasattr(torch.cuda, "clock_rate") else 1.965e9
+    print("%-36s %8.2f Gop/s/SM  = %6.2f thread-instr/clk/SM at %.2f GHz%s"
+          % (name, per_s / sms / 1e9, per_s / sms / clk, clk / 1e9,
+             "  -> %.1f SM-sub-partition cycles per warp-step" % (clk * 4 * 32 / (per_s / sms)) if mode == 11 else ""), flush=True)
