@@ -1076,7 +1076,9 @@ def main():
                                          "frac": (g["value"] / ws) / (len(g["cells_nf"]) / sum(1.0 / mix[nf] for nf in g["cells_nf"])),
                                          "per_fp32_count": {str(k): v for k, v in mix.items()},
                                          "note": "6 MUFU + 9 IMAD.WIDE.U32 + NF FP32 + 10 LOP3 + 2 I2FP per chain-step as independent chains "
-                                                 "(psgla_selftest_pipe_rate 100 + NF), NF = 21 / 23 (diagonal cells, PSGLA / PnP-ULA), 26 / 28 (cross prior)"},
+                                                 "(psgla_selftest_pipe_rate 100 + NF), NF = 21 / 23 (diagonal cells, PSGLA / PnP-ULA), 26 / 28 (cross prior); "
+                                                 "the probe's own loop issues ~8 % more LOP3 / IADD than the kernel, so it estimates the ceiling "
+                                                 "slightly from below and frac can read a little above 1"},
                      "launch_ms": g["total_ms"] / K / g["launches_per_step"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_gmm2d_lean_full.txt)
                      "traffic": 8.03e6 if args.chains == 1000000 else None,
