@@ -171,3 +171,34 @@ def test_wasserstein_unequal_sizes_solves_the_transport_lp():
     assert abs(P.Wasserstein_distance(x, y, rng=np.random.default_rng(0)) - 0.5) < 1e-9  # 1/6 and 1/3 of the mass move one unit
     un = P.Wasserstein_distance(a[:59], b, rng=np.random.default_rng(1))
     assert abs(un - eq) < 0.1 * eq
+
+
+def test_compiled_reference_loader_and_reference_arm(tmp_path):
+    """oracle/_ref/*.pycode (the reference's modules compiled by build(), what the GPU box loads) must behave like the sources:
+    with /root/reference hidden, the golden PSGLA trajectory row still comes out, and `bench.py --impl reference` (the CPU arm
+    the driver runs) prints one JSON line of kind "reference"."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from oracle import ref_loader
+    if not ref_loader._compiled_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    env = dict(os.environ, PSGLA_REFERENCE_ROOT=str(tmp_path / "nowhere"))
+    code = ("import numpy as np\n"
+            "from oracle import ref_loader as r\n"
+            "assert r.reference_kind() == 'compiled'\n"
+            "ns, u = r.load_sampling_2D(), r.load_utils_2D()\n"
+            "D = u.Theorical_MMSE(*u.gaussian_mixt_example('cross'))\n"
+            "np.random.seed(0)\n"
+            "X = ns.SnoPnP_ULA(6, np.array([0., -2.]), np.array([0., -2.]), 0.3, np.eye(2), 1, D, 2 / 3)\n"
+            "assert np.allclose(X[1], [0.1366241292, -0.6247715824], atol=1e-9), X[1]\n"
+            "assert callable(r.load_restoration_algorithms().psgla)\n")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    res = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-chain-steps", "300",
+                          "--skip-image"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == "langevin_chain_steps_per_sec_2d_gmm"
