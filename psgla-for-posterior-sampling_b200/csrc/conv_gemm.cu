@@ -650,13 +650,16 @@ static int cg_launch2_t(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static int max_clusters = 0;
+  static std::atomic<int> max_clusters_dev[kMaxDevices];  // per device: co-resident CTA pairs; 0 = not asked yet (also: the function attribute is unset)
+  std::atomic<int>& mc_slot = max_clusters_dev[current_device() % kMaxDevices];
+  int max_clusters = mc_slot.load(std::memory_order_acquire);
   if (!max_clusters) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
     int n = 0;
     PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE, RES2>, &cfg));
     max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
+    mc_slot.store(max_clusters, std::memory_order_release);
   }
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int pairs = ((m_tiles + 1) / 2) * p.quads * p.n_tiles_n;

@@ -759,7 +759,9 @@ static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaS
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static int max_clusters = 0;  // CTA pairs the device holds at once (one CTA per SM)
+  static std::atomic<int> max_clusters_dev[kMaxDevices];  // per device: CTA pairs it holds at once (one CTA per SM); 0 = not asked yet
+  std::atomic<int>& mc_slot = max_clusters_dev[current_device() % kMaxDevices];
+  int max_clusters = mc_slot.load(std::memory_order_acquire);
   if (!max_clusters) {
     PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ts2_kernel<NOUT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
@@ -767,6 +769,7 @@ static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaS
     int n = 0;
     PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv3x3_ts2_kernel<NOUT, RES>, &cfg));
     max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
+    mc_slot.store(max_clusters, std::memory_order_release);
     if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: conv3x3_ts2_kernel: %d co-resident CTA pairs (occupancy query %d)\n", max_clusters, n);
   }
   plan_items_pair(&p, max_clusters);
