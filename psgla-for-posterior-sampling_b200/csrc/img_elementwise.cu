@@ -513,11 +513,15 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
   const float* ab = aty + (long long)(aty_B > 1 ? b : 0) * 3 * plane + (long long)ch * plane;
   const int gx0 = x0 + 4 * q;
   const bool vec_ok = (W % 4 == 0) && gx0 + 3 < W;
-  // this thread's staged elements: e = tid + 192 i  ->  (channel, staged column); global offset without the row term
+  // this thread's staged elements: e = tid + 192 i  ->  (channel, staged column); global offset without the row term.
+  // When W and the halo are multiples of 4, a staged quad of columns is one aligned, unwrapped quad in global memory:
+  // 16-byte copies, (3 SROW / 4) / 192 = 2 per thread instead of 5 four-byte ones.
+  constexpr int NQ = (ROWSET / 4 + ATA_THREADS - 1) / ATA_THREADS;
+  const bool vstage = (K2 % 4 == 0) && (W % 4 == 0);
   unsigned goff[NE];
 #pragma unroll
   for (int i = 0; i < NE; ++i) {
-    const int e = tid + ATA_THREADS * i;
+    const int e = vstage ? 4 * (tid + ATA_THREADS * i) : tid + ATA_THREADS * i;  // first element of the quad / the element
     const int c = e / SROW, col = e - c * SROW;
     goff[i] = (e < ROWSET) ? (unsigned)((long long)c * plane + wrap(x0 - K2 + col, W)) : 0u;
   }
@@ -526,12 +530,23 @@ deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const f
     if (r < nrows) {
       const long long rowoff = (long long)wrap(y0 - K2 + r, H) * W;
       float* dst = ring + (r % NBUF) * ROWSET;
+      if (vstage) {
 #pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        const int e = tid + ATA_THREADS * i;
-        if (e < ROWSET) {
-          const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + e);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(xb + rowoff + goff[i]) : "memory");
+        for (int i = 0; i < NQ; ++i) {
+          const int e = 4 * (tid + ATA_THREADS * i);
+          if (e < ROWSET) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xb + rowoff + goff[i]) : "memory");
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const int e = tid + ATA_THREADS * i;
+          if (e < ROWSET) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + e);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(xb + rowoff + goff[i]) : "memory");
+          }
         }
       }
       const int orow = r - 2 * K2;
@@ -833,7 +848,7 @@ static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const
                       const float* noise, float* out, void* den_in, cudaStream_t st) {
   // rows per block: two blocks are resident per SM (registers) and hide each other's latencies, so the launch takes about
   // ceil(blocks / (2 SMs)) rounds of RH + 2 K2 row steps (measured at 32 chains of 256 x 256, l = 4: RH = 8 / 16 / 32 / 64 / 128
-  // -> 87 / 71 / 64 / 87 / 163 us; the four-pass kernel 83 us)
+  // -> 83 / 66 / 59 / 82 / 152 us; the four-pass kernel 84 us)
   const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = 2 * num_sms();
   int best_rh = 16;
   long long best = -1;

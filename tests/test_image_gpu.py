@@ -216,6 +216,21 @@ def test_pre_deblur_ata_philox_and_batched_observation():
                                                   None if noise is None else noise.data_ptr(), base.data_ptr(), den_in.data_ptr(), None), "ata")
         outs.append(base)
     assert torch.equal(outs[0], outs[1])
+    # canaries: outputs carved out of larger sentinel-filled buffers (odd sizes, width not a multiple of 4, strips > 256 columns)
+    for Hc, Wc in ((19, 37), (9, 530)):
+        xc, zc, imc = _pre_inputs(2, Hc, Wc, seed=8)
+        ddc, _, yc = P.make_deblurring(imc, l=3, blur_type="gaussian", si=1.2)
+        atyc = ddc.AT(yc)
+        n = 2 * 3 * Hc * Wc
+        big = torch.full((n + 2048,), 1234.5, device="cuda")
+        bigd = torch.full((2 * Hc * Wc * 16 + 4096,), 7.0, device="cuda", dtype=torch.bfloat16)
+        base_c, den_c = big[1024:1024 + n], bigd[2048:2048 + 2 * Hc * Wc * 16]
+        P._lib.check(lib.psgla_img_pre_deblur_ata(pre, P._lib.ImgShape(2, 3, Hc, Wc), xc.data_ptr(), ddc._taps_c, 3, atyc.data_ptr(), 1,
+                                                  zc.data_ptr(), base_c.data_ptr(), den_c.data_ptr(), None), "ata canary")
+        torch.cuda.synchronize()
+        assert torch.all(big[:1024] == 1234.5) and torch.all(big[1024 + n:] == 1234.5)
+        assert torch.all(bigd[:2048] == 7.0) and torch.all(bigd[2048 + 2 * Hc * Wc * 16:] == 7.0)
+        assert torch.isfinite(base_c).all() and not torch.any(base_c == 1234.5)
     want = x - 0.3 * (dd.A(dd.A(x)) - aty) + 0.7 * z
     assert (outs[0] - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
 
