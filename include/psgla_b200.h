@@ -259,6 +259,12 @@ int psgla_conv3x3_layer(const void* packed_dev, int depth, int layer, psgla_img_
  * DnCNN), channels 4..15 zero. */
 int psgla_img_to_nhwc16(psgla_img_shape shape, const float* x_dev, float c3, void* out_dev, void* stream);
 
+/* In-place replication padding of a bf16 NHWC16 batch [B][padded.H][padded.W][16]: pixels with y >= H or x >= W copy the nearest
+ * valid pixel (KAIR's test_pad, what the DRUNet of the reference -- deepinv.models.DRUNet, sampling_images.py:136 -- applies to
+ * inputs whose sides are not multiples of 8).  The samplers call it on the denoiser input before every DRUNet application of a
+ * problem that was padded to multiples of 8. */
+int psgla_img_pad_replicate_nhwc16(psgla_img_shape padded, int H, int W, void* img_dev, void* stream);
+
 /* tcgen05 descriptor self-test (development aid): runs a 128 x 64 x 64 GEMM tile whose A operand starts `row_shift`
  * rows into a 128B-swizzled shared-memory buffer.  mode 0: A from shared memory, shift = descriptor start address;
  * mode 1: same with a base-offset field (kept for reference, wrong on sm_100a); mode 2: A copied to tensor memory.

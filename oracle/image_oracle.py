@@ -104,8 +104,9 @@ class DRUNet(nn.Module):
     deepinv).  ``forward(x, sigma)`` concatenates a constant noise-level channel and returns the *denoised image*
     (no global residual).  State-dict keys follow the ``drunet_color.pth`` checkpoint: ``m_head``, ``m_down{1,2,3}.{0..3}
     .res.{0,2}``, ``m_down{k}.4`` (2x2 stride-2 conv), ``m_body.{0..3}``, ``m_up{k}.0`` (2x2 stride-2 transposed conv),
-    ``m_up{k}.{1..4}``, ``m_tail``.  H and W must be multiples of 8 (deepinv pads internally; the rule is unverifiable
-    here, so callers crop)."""
+    ``m_up{k}.{1..4}``, ``m_tail``.  Inputs whose H or W is not a multiple of 8 are replication-padded at the bottom / right,
+    denoised and cropped -- KAIR's ``utils_model.test_pad`` (``ReplicationPad2d((0, pw, 0, ph))``), the rule deepinv applies to
+    small inputs [recalled; its rule for large inputs, a 4-way overlapping split, is not restated]."""
 
     def __init__(self, in_channels=3, out_channels=3, nc=(64, 128, 256, 512), nb=4):
         super().__init__()
@@ -122,6 +123,10 @@ class DRUNet(nn.Module):
     def forward(self, x, sigma):
         if isinstance(sigma, torch.Tensor):
             sigma = float(sigma.reshape(-1)[0])
+        H0, W0 = x.shape[2], x.shape[3]
+        ph, pw = (-H0) % 8, (-W0) % 8
+        if ph or pw:
+            return self.forward(F.pad(x, (0, pw, 0, ph), mode="replicate"), sigma)[:, :, :H0, :W0]
         noise_map = torch.full((x.shape[0], 1, x.shape[2], x.shape[3]), float(sigma), dtype=x.dtype, device=x.device)
         x0 = torch.cat((x, noise_map), 1)
         x1 = self.m_head(x0)

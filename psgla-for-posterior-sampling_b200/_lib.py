@@ -89,6 +89,7 @@ SIGNATURES = {
     "psgla_dncnn_last_layer_post_next": (_int, [_int, _vp, ImgShape, _vp, _vp, C.POINTER(PostParams), _vp, _vp, _vp, _vp,
                                                 C.POINTER(NextPre), _vp]),
     "psgla_conv3x3_layer": (_int, [_vp, _int, _int, ImgShape, _vp, _vp, _int, _vp]),
+    "psgla_img_pad_replicate_nhwc16": (_int, [ImgShape, _int, _int, _vp, _vp]),
     "psgla_img_to_nhwc16": (_int, [ImgShape, _vp, C.c_float, _vp, _vp]),
     "psgla_img_metrics_workspace_bytes": (_sz, [_int]),
     "psgla_img_psnr_ssim": (_int, [ImgShape, _vp, _vp, C.c_float, _vp, _sz, _vp, _vp, _vp]),

@@ -701,6 +701,31 @@ to_nhwc16_kernel(int B, int H, int W, const float* __restrict__ x, float c3, __n
   store_nhwc16(out + g * 16, xp[0], xp[plane], xp[2 * plane], c3);
 }
 
+// Replication padding of a bf16 NHWC16 image batch in place: pixels with y >= H or x >= W (the pad a U-Net needs to reach a
+// multiple of 8) copy the nearest valid pixel -- KAIR's test_pad (ReplicationPad2d on the bottom / right).
+__global__ void __launch_bounds__(256)
+pad_replicate_nhwc16_kernel(int B, int Hp, int Wp, int H, int W, __nv_bfloat16* __restrict__ img) {
+  const int n_pad_per_chain = Hp * Wp - H * W;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n_pad_per_chain * B) return;
+  const int b = (int)(g / n_pad_per_chain);
+  int k = (int)(g % n_pad_per_chain);
+  int y, x;
+  if (k < H * (Wp - W)) {  // right band of the valid rows
+    y = k / (Wp - W);
+    x = W + k % (Wp - W);
+  } else {                 // bottom band, full padded width
+    k -= H * (Wp - W);
+    y = H + k / Wp;
+    x = k % Wp;
+  }
+  const int ys = min(y, H - 1), xs = min(x, W - 1);
+  const uint4* src = reinterpret_cast<const uint4*>(img + (((long long)b * Hp + ys) * Wp + xs) * 16);
+  uint4* dst = reinterpret_cast<uint4*>(img + (((long long)b * Hp + y) * Wp + x) * 16);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
 int fill_pre(const psgla_pre_params* p, PreArgs* a) {
   PSGLA_REQUIRE(p != nullptr, "null psgla_pre_params");
   PSGLA_REQUIRE(p->alg == PSGLA_ALG_PSGLA || p->alg == PSGLA_ALG_PNPULA, "alg=%d is not a PSGLA_ALG_* value", p->alg);
@@ -951,6 +976,18 @@ extern "C" int psgla_img_noise_torch_cuda(int64_t numel, uint64_t seed, uint64_t
                 "psgla_img_noise_torch_cuda: bad argument");
   noise_torch_cuda_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(numel, seed, offset, threads,
                                                                                             out_dev);
+  PSGLA_CUDA_TRY(cudaGetLastError());
+  return PSGLA_OK;
+}
+
+extern "C" int psgla_img_pad_replicate_nhwc16(psgla_img_shape padded, int H, int W, void* img_dev, void* stream) {
+  int rc = check_img(padded);
+  if (rc) return rc;
+  PSGLA_REQUIRE(img_dev && H >= 1 && W >= 1 && H <= padded.H && W <= padded.W, "psgla_img_pad_replicate_nhwc16: bad argument");
+  const long long n = ((long long)padded.H * padded.W - (long long)H * W) * padded.B;
+  if (n == 0) return PSGLA_OK;
+  pad_replicate_nhwc16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(padded.B, padded.H, padded.W, H, W,
+                                                                                            (__nv_bfloat16*)img_dev);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
 }

@@ -284,8 +284,8 @@ class DRUNet:
         """D(x; sigma), fp32 [B,3,H,W] in and out.  The U-Net halves the resolution three times, so H and W must be multiples
         of 8; other sizes (CBSD68's 481 x 321) are replication-padded at the bottom / right to the next multiple, denoised and
         cropped -- KAIR's ``test_pad`` rule, which is what deepinv applies to small inputs (its rule for large ones, a 4-way
-        overlapping split, cannot be verified offline: a documented deviation).  The fused sampler path (``apply_post``) does
-        not pad: crop or pad the PROBLEM for psgla / pnpula (e.g. 481 x 321 -> 480 x 320)."""
+        overlapping split, cannot be verified offline: a documented deviation).  The samplers apply the same per-call padding to
+        inpainting problems (restoration_algorithms._Run); deblurring problems must be cropped to multiples of 8."""
         if not x.is_cuda:
             raise RuntimeError("DRUNet.forward needs a CUDA tensor: there is no CPU path")
         sigma = float(sigma.reshape(-1)[0]) if isinstance(sigma, torch.Tensor) else float(sigma)

@@ -72,6 +72,23 @@ class _Run:
                              "planes per chain (the reference's --grayscale runs are out of scope)" % (tuple(init.shape),))
         self.squeeze = n_chains is None and x.shape[0] == 1
         B = int(n_chains) if n_chains is not None else int(x.shape[0])
+        # DRUNet halves the resolution three times.  Sides that are not multiples of 8 (CBSD68: 481 x 321) are handled like KAIR's
+        # test_pad, which deepinv's DRUNet applies per call: the network sees the image replication-padded at the bottom / right
+        # and its output is cropped.  Here the whole problem is carried at the padded size -- the pad region is unobserved
+        # (mask 0), its state never feeds back because the denoiser input's pad pixels are re-filled from the edge before every
+        # network application (psgla_img_pad_replicate_nhwc16) -- and every returned tensor is cropped.  Inpainting only: the
+        # circular blur of the deblurring problem is defined on the true image size.
+        self.crop = None
+        if isinstance(denoiser, DRUNet) and (x.shape[2] % 8 or x.shape[3] % 8):
+            if not isinstance(data_grad, InpaintingDataGrad):
+                raise RuntimeError("DRUNet needs H and W to be multiples of 8 for deblurring problems (crop the image, e.g. "
+                                   "481 x 321 -> 480 x 320); inpainting problems are padded internally")
+            self.crop = (int(x.shape[2]), int(x.shape[3]))
+            ph, pw = (-x.shape[2]) % 8, (-x.shape[3]) % 8
+            x = torch.nn.functional.pad(x, (0, pw, 0, ph), mode="replicate")
+            if noise is not None:
+                noise = torch.nn.functional.pad(noise.reshape((noise.shape[0], -1, 3) + self.crop).to(self.device, torch.float32),
+                                                (0, pw, 0, ph))
         self.X = x.expand(B, -1, -1, -1).contiguous().clone() if x.shape[0] != B else x.contiguous().clone()
         self.shape = _lib.ImgShape(B, 3, int(x.shape[2]), int(x.shape[3]))
         self.base = torch.empty_like(self.X)
@@ -126,9 +143,12 @@ class _Run:
             t = t.to(self.device)
             if t.dim() == 3:
                 t = t[None]
-            if t.dim() != 4 or t.shape[0] not in (1, B) or t.shape[1] not in channels or tuple(t.shape[2:]) != (H, W):
+            want = self.crop if self.crop is not None else (H, W)
+            if t.dim() != 4 or t.shape[0] not in (1, B) or t.shape[1] not in channels or tuple(t.shape[2:]) != want:
                 raise ValueError("%s has shape %s; expected [1 or %d, %s, %d, %d] to match init" %
-                                 (what, tuple(t.shape), B, "/".join(str(c) for c in channels), H, W))
+                                 (what, tuple(t.shape), B, "/".join(str(c) for c in channels), want[0], want[1]))
+            if self.crop is not None:  # zero pad: the pad region is unobserved
+                t = torch.nn.functional.pad(t, (0, W - want[1], 0, H - want[0]))
             return t.expand(-1, 3, -1, -1).contiguous()
 
         if isinstance(data_grad, DeblurDataGrad):
@@ -161,6 +181,8 @@ class _Run:
         self._pre_done_for = nxt
 
     def _out(self, t):
+        if self.crop is not None:
+            t = t[..., :self.crop[0], :self.crop[1]]
         return t[0] if self.squeeze else t
 
     def z_for(self, i):
@@ -211,6 +233,10 @@ class _Run:
             self._stamp(self._next_params, next_iteration)
             nxt = _lib.NextPre(C.pointer(self._next_params), _lib.ptr(self.mask), _lib.ptr(self.y), int(self.mask.shape[0]),
                                int(self.y.shape[0]), _lib.ptr(self.base), _lib.ptr(self.den_in))
+        if self.crop is not None:  # re-fill the pad pixels of the network input from the image edge (KAIR test_pad)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().psgla_img_pad_replicate_nhwc16(self.shape, self.crop[0], self.crop[1], _lib.ptr(self.den_in),
+                                                                     _lib.stream_ptr(self.device)), "psgla_img_pad_replicate_nhwc16")
         self.den.apply_post(self.shape, self.den_in, self.base, post, self.X, sample, self.mean, self.mean2, next_pre=nxt)
         if sample is not None:
             self.Xlist.append(self._out(sample))
