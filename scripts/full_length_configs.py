@@ -71,6 +71,7 @@ torch.cuda.empty_cache()
 # ---------------------------------------------------------------- configs[4]
 castle = P.load_image(os.path.join(ROOT, "tests", "golden", "set1c", "castle.png"))[0]
 dru = P.DRUNet(pretrained=P.random_drunet_state_dict(0))
+torch.cuda.reset_peak_memory_stats()
 n4 = 300 if quick else 10000
 prm4 = dict(P.sampler_params("psgla", den="DRUNet", lambd=25.0, N=n4))
 prm4["n_inter"] = prm4["n_inter_mmse"] = max(prm4["n_inter"], 1)  # the script's int(N / 1000) is 0 below N = 1000 (quick mode only)
