@@ -490,8 +490,10 @@ __device__ __forceinline__ void ata_vpass(float (&hring)[NT][4], const float (&o
   }
 }
 
-template <int K2, int MINB>  // K2 = 2 l: half-width of A^T A; MINB: resident blocks per SM the register budget is cut for
-__global__ void __launch_bounds__(ATA_THREADS, MINB)
+// Two blocks per SM (156 registers).  A 96-register build with three resident blocks spills part of the window: 86 us
+// instead of 58 (measured, scripts/blur_sweep.py).
+template <int K2>  // K2 = 2 l: half-width of A^T A
+__global__ void __launch_bounds__(ATA_THREADS, 2)
 deblur_ata_kernel(PreArgs a, const Taps2 k, int B, int H, int W, int RH, const float* __restrict__ x,
                   const float* __restrict__ aty, int aty_B, const float* __restrict__ noise, float* __restrict__ out,
                   __nv_bfloat16* __restrict__ den_in) {
@@ -868,13 +870,13 @@ static void ata_taps(const float* h, int l, Taps2* k) {
   }
 }
 
-template <int K2, int MINB>
-static int launch_ata_m(const PreArgs& a, const Taps2& k, psgla_img_shape s, const float* x, const float* aty, int aty_B,
+template <int K2>
+static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const float* x, const float* aty, int aty_B,
                       const float* noise, float* out, void* den_in, cudaStream_t st) {
   // rows per block: two blocks are resident per SM (registers) and hide each other's latencies, so the launch takes about
   // ceil(blocks / (2 SMs)) rounds of RH + 2 K2 row steps (measured at 32 chains of 256 x 256, l = 4: RH = 8 / 16 / 32 / 64 / 128
   // -> 83 / 66 / 59 / 82 / 152 us; the four-pass kernel 84 us)
-  const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = MINB * num_sms();
+  const int strips = (s.W + ATA_COLS - 1) / ATA_COLS, sms = 2 * num_sms();
   int best_rh = 16;
   long long best = -1;
   for (int rh = 8; rh <= 128; rh *= 2) {
@@ -891,21 +893,13 @@ static int launch_ata_m(const PreArgs& a, const Taps2& k, psgla_img_shape s, con
   static std::atomic<unsigned long long> attr_done{0};  // bit d: opted in on device d (a per-device function attribute)
   const unsigned long long dev_bit = 1ull << (current_device() & 63);
   if (smem > 48 * 1024 && !(attr_done.load(std::memory_order_acquire) & dev_bit)) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(deblur_ata_kernel<K2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(deblur_ata_kernel<K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
-  deblur_ata_kernel<K2, MINB><<<dim3(strips, (s.H + best_rh - 1) / best_rh, s.B), ATA_THREADS, smem, st>>>(
+  deblur_ata_kernel<K2><<<dim3(strips, (s.H + best_rh - 1) / best_rh, s.B), ATA_THREADS, smem, st>>>(
       a, k, s.B, s.H, s.W, best_rh, x, aty, aty_B, noise, out, (__nv_bfloat16*)den_in);
   PSGLA_CUDA_TRY(cudaGetLastError());
   return PSGLA_OK;
-}
-
-template <int K2>
-static int launch_ata(const PreArgs& a, const Taps2& k, psgla_img_shape s, const float* x, const float* aty, int aty_B,
-                      const float* noise, float* out, void* den_in, cudaStream_t st) {
-  const char* e = std::getenv("PSGLA_ATA_MINB");  // A/B: 3 = a 96-register build (part of the window spills) with 3 resident blocks
-  if (e && std::atoi(e) == 3) return launch_ata_m<K2, 3>(a, k, s, x, aty, aty_B, noise, out, den_in, st);
-  return launch_ata_m<K2, 2>(a, k, s, x, aty, aty_B, noise, out, den_in, st);
 }
 
 extern "C" int psgla_img_pre_deblur_ata(const psgla_pre_params* p, psgla_img_shape s, const float* x_dev,

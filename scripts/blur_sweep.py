@@ -37,10 +37,7 @@ def time_pre(label):
 os.environ["PSGLA_BLUR_4PASS"] = "1"
 time_pre("four-pass")
 os.environ["PSGLA_BLUR_4PASS"] = "0"
-for minb in ("2", "3"):
-    os.environ["PSGLA_ATA_MINB"] = minb
-    os.environ.pop("PSGLA_ATA_RH", None)
-    for rh in (0, 8, 16, 32, 64, 128):
-        if rh:
-            os.environ["PSGLA_ATA_RH"] = str(rh)
-        time_pre("A^T A %s blocks/SM, rows/block %s" % (minb, rh or "auto"))
+for rh in (0, 8, 16, 32, 64, 128):
+    if rh:
+        os.environ["PSGLA_ATA_RH"] = str(rh)
+    time_pre("A^T A rows/block %s" % (rh or "auto"))
