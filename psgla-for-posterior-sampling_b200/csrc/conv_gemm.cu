@@ -316,16 +316,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // of 130 pixels (halo left and right) and the weights of the three taps of that row (dx = 0, 1, 2, one 3-D box), and serves
 // 12 MMAs whose A descriptors start dx rows into the box -- a third of the activation traffic from L2 per MMA.  Without it
 // the 128-channel layers (4 MMAs of 64 cycles per 16 KB A box) sit at 0.65 of the tensor peak on L2 -> SM bandwidth.
-template <int N_TILE, bool REUSE>
+//
+// WRES (128 -> 128 channels, REUSE geometry): the layer's weights stay RESIDENT in shared memory -- this CTA's 64 output
+// channels x 128 input channels x 9 taps = 144 KB, loaded once per launch before the wait on the previous layer -- and the
+// ring carries activations only.  With streamed weights an item pulls 147 KB of weights and 100 KB of activations per CTA
+// through L2 -> SM (5 GB per layer at 64 chains of 160 x 240: the layer ran at 1 410 TFLOP/s where the 256-channel layers,
+// twice the MMA work per byte, reach 1 530, and a residual input cost its full read time on top, 514 -> 637 us).
+template <int N_TILE, bool REUSE, bool WRES = false>
 struct CgCfg2 {
+  static_assert(!WRES || (REUSE && N_TILE == 128), "resident weights: the 128-channel 3x3 layers only");
   static constexpr int THREADS = 64 + 32 * CG_EPI_WARPS;
   static constexpr int A_BOX_BYTES = REUSE ? 130 * 128 : 128 * 128;
   static constexpr int A_BYTES = REUSE ? 17 * 1024 : 128 * 128;
   static constexpr int TAP_BYTES = (N_TILE / 2) * 128;          // this CTA's half of the N tile, one tap
-  static constexpr int B_BYTES = (REUSE ? 3 : 1) * TAP_BYTES;
+  static constexpr int B_BYTES = WRES ? 0 : (REUSE ? 3 : 1) * TAP_BYTES;
+  static constexpr int W_KBLOCKS = 2;                            // WRES: Cin = 128
+  static constexpr int W_BYTES = WRES ? 9 * W_KBLOCKS * TAP_BYTES : 0;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = (225280 / STAGE_BYTES) > 8 ? 8 : (225280 / STAGE_BYTES);
-  static constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
+  static constexpr int NSTAGE = ((225280 - W_BYTES) / STAGE_BYTES) > 8 ? 8 : ((225280 - W_BYTES) / STAGE_BYTES);
+  static constexpr int OFF_W = NSTAGE * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_W + W_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = CG_NACC * N_TILE;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
@@ -353,10 +363,10 @@ __device__ __forceinline__ CgItem cg_decode2(const CgParams& p, int item) {
 
 // RES2: a second residual tensor (U-Net skip, one layer per scale) is prefetched like the first; its own instantiation,
 // so that its 64 extra registers do not weigh on the other layers.
-template <int N_TILE, bool REUSE, bool RES2>
-__global__ void __launch_bounds__((CgCfg2<N_TILE, REUSE>::THREADS), 1)
+template <int N_TILE, bool REUSE, bool RES2, bool WRES = false>
+__global__ void __launch_bounds__((CgCfg2<N_TILE, REUSE, WRES>::THREADS), 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const CgParams p) {
-  using Cfg = CgCfg2<N_TILE, REUSE>;
+  using Cfg = CgCfg2<N_TILE, REUSE, WRES>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -365,7 +375,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tfull = empty + NSTAGE;                                   // both (multicast): accumulator complete
   uint64_t* tempty = tfull + CG_NACC;                                 // leader: both epilogues drained the stage
   uint64_t* done = tempty + CG_NACC;                                  // both (multicast): all MMAs of the launch completed
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* wbar = done + 1;                                          // WRES, local: this CTA's half of the weights landed
+  uint64_t* wready = wbar + 1;                                        // WRES, leader: the peer's half landed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(wready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -382,6 +394,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&tempty[i], 8);
     }
     mbar_init(done, 1);
+    mbar_init(wbar, 1);
+    mbar_init(wready, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -402,10 +416,31 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t full_c = mapa_shared(smem_u32(full), 0);
       const uint32_t stage_tx = 2u * (uint32_t)((REUSE ? Cfg::A_BOX_BYTES : p.PX * p.ROWS * 128) + Cfg::B_BYTES);
       const int nrow0 = (int)rank * (N_TILE / 2);
+      if (WRES) {  // the whole layer's weights for this CTA's output channels: box (dy, kb) = taps 3 dy .. 3 dy + 2, 64 input channels
+        mbar_expect_tx(wbar, (uint32_t)Cfg::W_BYTES);
+        for (int dy = 0; dy < 3; ++dy)
+          for (int kb = 0; kb < Cfg::W_KBLOCKS; ++kb)
+            tma_load_3d(smem + Cfg::OFF_W + (dy * Cfg::W_KBLOCKS + kb) * 3 * Cfg::TAP_BYTES, &map_w, wbar, kb * 64, nrow0, dy * 3);
+        if (rank != 0) {
+          mbar_wait(wbar, 0);
+          mbar_arrive_cluster(mapa_shared(smem_u32(wready), 0));
+        }
+      }
       griddep_wait();
       uint32_t L = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const CgItem c = cg_decode2(p, item);
+        if (WRES) {
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int kb = 0; kb < Cfg::W_KBLOCKS; ++kb, ++L) {
+              const uint32_t slot = L % NSTAGE;
+              mbar_wait(&empty[slot], ((L / NSTAGE) & 1) ^ 1);
+              if (rank == 0) mbar_expect_tx(&full[slot], 2u * (uint32_t)Cfg::A_BOX_BYTES);
+              tma_load_4d_2sm(smem + slot * Cfg::STAGE_BYTES, &map_a, full_c + slot * 8u, kb * 64, c.x0 - 1, c.y0 + dy - 1, c.b);
+            }
+          }
+          continue;
+        }
         if (REUSE) {
           for (int dy = 0; dy < 3; ++dy) {
             for (int kb = 0; kb < p.kblocks; ++kb, ++L) {
@@ -448,6 +483,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(256, N_TILE);
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
       const uint32_t smem_lo = (smem_u32(smem) >> 4) | 0x10000u;
+      if (WRES) {
+        mbar_wait(wbar, 0);
+        mbar_wait_cluster(wready, 0);
+        tc_fence_after();
+      }
       uint32_t L = 0, T = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++T) {
         const uint32_t acc = T % CG_NACC;
@@ -460,7 +500,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_lo = smem_lo + slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
-            const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
+            const uint32_t b_lo = WRES ? smem_lo + (uint32_t)((Cfg::OFF_W + it * 3 * Cfg::TAP_BYTES) >> 4)  // it = dy * 2 + kb
+                                       : a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
             if (REUSE) {
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
@@ -513,16 +554,24 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         xo = 2 * xg + (c.q & 1);
       }
       const size_t off = (((size_t)c.b * p.Hout + yo) * p.Wout + xo) * p.Cout + (size_t)c.n0 * N_TILE;
+      // merged transposed conv (quads == 1): the N axis is (quadrant, channel), a 32-column chunk lies in one quadrant
+      const bool upm = p.mode == CG_UP2 && p.quads == 1;
+      auto chunk_off = [&](int ch) -> size_t {
+        if (!upm) return off + (size_t)(ch * 32);
+        const int n = c.n0 * N_TILE + ch * 32;
+        const int q = n / p.Cout, cc = n - q * p.Cout;
+        return (((size_t)c.b * p.Hout + 2 * yg + (q >> 1)) * p.Wout + 2 * xg + (q & 1)) * p.Cout + cc;
+      };
       const bool has_res = valid && p.res1 != nullptr;
       const bool has_res2 = RES2 && valid && p.res2 != nullptr;
       uint4 rr[16], rr2[RES2 ? 16 : 1];
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rr[j] = *reinterpret_cast<const uint4*>(p.res1 + off + j * 8);
+        for (int j = 0; j < 16; j += 2) ldg256(p.res1 + off + j * 8, rr[j], rr[j + 1]);
       }
       if (RES2 && has_res2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rr2[RES2 ? j : 0] = *reinterpret_cast<const uint4*>(p.res2 + off + j * 8);
+        for (int j = 0; j < 16; j += 2) ldg256(p.res2 + off + j * 8, rr2[RES2 ? j : 0], rr2[RES2 ? j + 1 : 0]);
       }
       mbar_wait(&tfull[acc], (T / CG_NACC) & 1);
       tc_fence_after();
@@ -540,27 +589,30 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_c + acc * 8u);
           }
+          const size_t choff = chunk_off(ch);
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
+            for (int j2 = 0; j2 < 2; ++j2) {  // 32 bytes = 16 channels per access
+              uint4 w[2];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
-              const size_t o = off + ch * 32 + j * 8;
-              if (has_res) {
-                cg_add_bf16x8(f, rr[c4 * 4 + j]);
-                if (hb + 1 < NB) rr[c4 * 4 + j] = *reinterpret_cast<const uint4*>(p.res1 + o + 128);
+              for (int h = 0; h < 2; ++h) {
+                const int j = 2 * j2 + h;
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
+                if (has_res) cg_add_bf16x8(f, rr[c4 * 4 + j]);
+                if (RES2 && has_res2) cg_add_bf16x8(f, rr2[RES2 ? c4 * 4 + j : 0]);
+                w[h].x = cg_pack(f[0], f[1], relu);
+                w[h].y = cg_pack(f[2], f[3], relu);
+                w[h].z = cg_pack(f[4], f[5], relu);
+                w[h].w = cg_pack(f[6], f[7], relu);
               }
-              if (RES2 && has_res2) {
-                cg_add_bf16x8(f, rr2[RES2 ? c4 * 4 + j : 0]);
-                if (hb + 1 < NB) rr2[RES2 ? c4 * 4 + j : 0] = *reinterpret_cast<const uint4*>(p.res2 + o + 128);
+              const size_t o = choff + j2 * 16;
+              if (hb + 1 < NB) {
+                if (has_res) ldg256(p.res1 + o + 128, rr[c4 * 4 + 2 * j2], rr[c4 * 4 + 2 * j2 + 1]);
+                if (RES2 && has_res2) ldg256(p.res2 + o + 128, rr2[RES2 ? c4 * 4 + 2 * j2 : 0], rr2[RES2 ? c4 * 4 + 2 * j2 + 1 : 0]);
               }
-              uint4 w;
-              w.x = cg_pack(f[0], f[1], relu);
-              w.y = cg_pack(f[2], f[3], relu);
-              w.z = cg_pack(f[4], f[5], relu);
-              w.w = cg_pack(f[6], f[7], relu);
-              *reinterpret_cast<uint4*>(p.out + o) = w;
+              stg256(p.out + o, w[0], w[1]);
             }
           }
         }
@@ -634,9 +686,9 @@ static int cg_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CgParam
   return PSGLA_OK;
 }
 
-template <int N_TILE, bool REUSE, bool RES2>
+template <int N_TILE, bool REUSE, bool RES2, bool WRES = false>
 static int cg_launch2_t(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p, cudaStream_t st) {
-  using Cfg = CgCfg2<N_TILE, REUSE>;
+  using Cfg = CgCfg2<N_TILE, REUSE, WRES>;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -654,10 +706,10 @@ static int cg_launch2_t(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p
   std::atomic<int>& mc_slot = max_clusters_dev[current_device() % kMaxDevices];
   int max_clusters = mc_slot.load(std::memory_order_acquire);
   if (!max_clusters) {
-    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PSGLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<N_TILE, REUSE, RES2, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
     int n = 0;
-    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE, RES2>, &cfg));
+    PSGLA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv_gemm2_kernel<N_TILE, REUSE, RES2, WRES>, &cfg));
     max_clusters = n > 0 ? std::min(n, num_sms() / 2) : num_sms() / 2;
     mc_slot.store(max_clusters, std::memory_order_release);
   }
@@ -665,13 +717,13 @@ static int cg_launch2_t(const CUtensorMap& ma, const CUtensorMap& mw, CgParams p
   const int pairs = ((m_tiles + 1) / 2) * p.quads * p.n_tiles_n;
   p.n_items = 2 * pairs;
   cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<N_TILE, REUSE, RES2>, ma, mw, p));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<N_TILE, REUSE, RES2, WRES>, ma, mw, p));
   return PSGLA_OK;
 }
 
-template <int N_TILE, bool REUSE>
+template <int N_TILE, bool REUSE, bool WRES = false>
 static int cg_launch2(const CUtensorMap& ma, const CUtensorMap& mw, const CgParams& p, cudaStream_t st) {
-  return p.res2 ? cg_launch2_t<N_TILE, REUSE, true>(ma, mw, p, st) : cg_launch2_t<N_TILE, REUSE, false>(ma, mw, p, st);
+  return p.res2 ? cg_launch2_t<N_TILE, REUSE, true, WRES>(ma, mw, p, st) : cg_launch2_t<N_TILE, REUSE, false, WRES>(ma, mw, p, st);
 }
 
 // One layer.  in: bf16 NHWC [B][Hin][Win][Cin]; w: bf16 [taps][Cout][Cin]; out: bf16 NHWC (CONV3: same extent, DOWN2:
@@ -682,11 +734,13 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
   PSGLA_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0,
                 "conv_gemm_layer: channels must be multiples of 64 (got %d -> %d), extents positive", Cin, Cout);
   PSGLA_REQUIRE(w && in && out, "conv_gemm_layer: null pointer");
+  PSGLA_REQUIRE(((uintptr_t)out | (uintptr_t)res1 | (uintptr_t)res2) % 32 == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)w % 16 == 0,
+                "conv_gemm_layer: out / residual tensors must be 32-byte aligned, in / weights 16-byte aligned");
   PSGLA_REQUIRE(mode != CG_DOWN2 || (Hin % 2 == 0 && Win % 2 == 0), "stride-2 conv needs even extents (got %d x %d)", Hin, Win);
   CgParams p{};
   p.mode = mode;
   p.taps = mode == CG_CONV3 ? 9 : (mode == CG_DOWN2 ? 4 : 1);
-  p.quads = mode == CG_UP2 ? 4 : 1;
+  p.quads = mode == CG_UP2 ? 4 : 1;  // (1 once the pair kernel merges the quadrants into the N axis, below)
   p.kblocks = Cin / 64;
   p.B = B, p.Hin = Hin, p.Win = Win, p.Cin = Cin, p.Cout = Cout;
   p.Hg = mode == CG_DOWN2 ? Hin / 2 : Hin;
@@ -714,7 +768,19 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
     const char* e = getenv("PSGLA_CG_PAIR");
     cg_pair = (e && e[0] == '0') ? 0 : 1;
   }
-  const int n_tile = (!ts && Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // Transposed conv on the pair kernel: ONE GEMM with N = 4 Cout -- the weights [quadrant][Cout][Cin] are a [4 Cout][Cin]
+  // matrix as they lie, the epilogue scatters column n to quadrant n / Cout -- so an A tile is loaded once instead of once per
+  // quadrant and the 128 -> 64 layer gets 256-column tiles on the CTA pair instead of 64-column ones on one CTA.
+  // PSGLA_CG_UPMERGE=0: one GEMM per quadrant (A/B runs).
+  static int cg_upmerge = -1;
+  if (cg_upmerge < 0) {
+    const char* e = getenv("PSGLA_CG_UPMERGE");
+    cg_upmerge = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool upmerge = mode == CG_UP2 && cg_pair && !ts && cg_upmerge;
+  const int n_cols = upmerge ? 4 * Cout : Cout;
+  if (upmerge) p.quads = 1;
+  const int n_tile = (!ts && n_cols % 256 == 0) ? 256 : (n_cols % 128 == 0 ? 128 : 64);
   const bool pair = cg_pair && !ts && n_tile >= 128;
   // one 130-pixel row box for the three horizontal taps (CgCfg2<., true>): 3x3 layers with rows of >= 128 pixels
   static int cg_reuse = -1;
@@ -724,7 +790,7 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
   }
   const bool reuse = pair && cg_reuse && mode == CG_CONV3 && p.PX == 128 && p.ROWS == 1;
   p.reverse = pair ? next_layer_direction() : 0;
-  p.n_tiles_n = Cout / n_tile;
+  p.n_tiles_n = n_cols / n_tile;
   p.n_items = B * p.tiles_y * p.tiles_x * p.quads * p.n_tiles_n;
   p.relu = relu;
   p.res1 = (const __nv_bfloat16*)res1;
@@ -747,14 +813,21 @@ int conv_gemm_layer(int mode, int B, int Hin, int Win, int Cin, int Cout, const 
   }
   if (rc) return rc;
   {
-    const int taps_total = mode == CG_UP2 ? 4 : p.taps;
-    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps_total};
-    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    const int taps_total = upmerge ? 1 : (mode == CG_UP2 ? 4 : p.taps);
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)n_cols, (cuuint64_t)taps_total};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)n_cols * Cin * 2};
     const int box_n = pair ? n_tile / 2 : n_tile;  // a CTA of a pair streams half of the N tile
     const cuuint32_t box[3] = {64, (cuuint32_t)box_n, reuse ? 3u : 1u};
-    rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, Cout, taps_total, box_n, reuse ? 3 : 1}, 3, dims, strides, box);
+    rc = cg_cached_map(&mw, CgMapKey{w, 3, Cin, n_cols, taps_total, box_n, reuse ? 3 : 1}, 3, dims, strides, box);
   }
   if (rc) return rc;
+  // resident weights for the 128 -> 128 channel layers (CgCfg2<128, true, true>); PSGLA_CG_WRES=0: streamed (A/B runs)
+  static int cg_wres = -1;
+  if (cg_wres < 0) {
+    const char* e = getenv("PSGLA_CG_WRES");
+    cg_wres = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (reuse && cg_wres && Cin == 128 && Cout == 128) return cg_launch2<128, true, true>(ma, mw, p, st);
   if (reuse) return n_tile == 256 ? cg_launch2<256, true>(ma, mw, p, st) : cg_launch2<128, true>(ma, mw, p, st);
   if (pair) return n_tile == 256 ? cg_launch2<256, false>(ma, mw, p, st) : cg_launch2<128, false>(ma, mw, p, st);
   if (n_tile == 256) return cg_launch<256, false>(ma, mw, p, st);

@@ -192,6 +192,18 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint4 v) {
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per lane.  With one pixel per lane and 16-byte
+// accesses every request touches 32 half sectors; the L2 then sees twice the transactions for the same bytes.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // returns once every prerequisite grid has completed and its memory is visible (no-op without the launch attribute)
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -52,6 +52,7 @@ def _tol(ref):
     (1, 5, 128, 128, 128, 1, True),    # CTA-pair kernel, one 130-pixel row box for the three horizontal taps; odd M-tile count
     (3, 3, 300, 128, 128, 2, True),    # same with three strips per row (ragged last strip), 27 M tiles
     (1, 4, 256, 256, 256, 0, False),   # row-box form at N tile 256
+    (4, 80, 256, 128, 128, 1, True),   # resident-weights form: 320 tile pairs, several per CTA pair (activation ring wraps)
 ])
 def test_conv3x3_general(B, H, W, Cin, Cout, res, relu):
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -79,7 +80,8 @@ def test_strided_down_conv(B, H, W, Cin, Cout):
     assert (got - ref).abs().max().item() <= _tol(ref)
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 20, 128, 64, 0), (1, 4, 4, 512, 256, 0), (1, 3, 130, 256, 128, 0)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 20, 128, 64, 0), (1, 4, 4, 512, 256, 0), (1, 3, 130, 256, 128, 0),
+                                                 (3, 40, 136, 128, 64, 0)])  # 240 ragged tile pairs, quadrants merged into N
 def test_transposed_up_conv(B, H, W, Cin, Cout, res):
     g = torch.Generator(device="cuda").manual_seed(2)
     x = _bf(torch.randn(B, Cin, H, W, device="cuda", generator=g))
