@@ -995,14 +995,31 @@ extern "C" int psgla_dncnn_residual_post_next(int depth, const void* packed_dev,
       if (rc) return rc;
       cur = ws[(depth - 2) & 1];
     } else {
+      int wsel = 0;  // the buffer the next layer writes
       for (int l = 0; l < depth - 1; ++l) {
         const LayerInfo li = layer_info(depth, l);
+        if (l >= 1 && l + 1 < depth - 1 && conv_use_ts() && conv_use_pair()) {
+          // few chains: two hidden layers per launch (conv_fused2.cu), the intermediate rows never leave the SM pair
+          const LayerInfo l2 = layer_info(depth, l + 1);
+          int fused = 0;
+          rc = conv64_hidden_fused2(cur, ws[wsel], packed + li.w_off, reinterpret_cast<const float*>(packed + li.b_off),
+                                    packed + l2.w_off, reinterpret_cast<const float*>(packed + l2.b_off), shape.B, shape.H, shape.W,
+                                    &fused, st);
+          if (rc) return rc;
+          if (fused) {
+            cur = ws[wsel];
+            wsel ^= 1;
+            ++l;
+            continue;
+          }
+        }
         ConvParams pl = base_params(shape, packed, li);
         pl.relu = 1;
         pl.reverse = alternate_items() ? (l & 1) : 0;
-        rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[l & 1], pl, st) : launch_hidden64(cur, ws[l & 1], pl, st);
+        rc = (l == 0) ? launch_conv<16, 64, EPI_HIDDEN>(cur, ws[wsel], pl, st) : launch_hidden64(cur, ws[wsel], pl, st);
         if (rc) return rc;
-        cur = ws[l & 1];
+        cur = ws[wsel];
+        wsel ^= 1;
       }
     }
   }

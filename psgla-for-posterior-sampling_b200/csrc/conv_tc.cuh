@@ -546,6 +546,10 @@ struct ConvTsCfg {
 // host helpers defined in conv_tc.cu
 int get_act_tensor_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int box_w);
 void plan_items(ConvParams* p);
+// conv_fused2.cu: two hidden layers (both conv + bias + ReLU) in one launch when the shape is a single wave of CTA pairs
+// (few chains); *applicable = 0 and nothing launched otherwise
+int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const float* b1, const uint8_t* w2, const float* b2, int B,
+                         int H, int W, int* applicable, cudaStream_t st);
 // experiments.cu: the 18 hidden layers of DnCNN as one persistent launch (PSGLA_CHAIN=1)
 int launch_hidden_chain(void* buf0, void* buf1, int n_layers, const uint8_t* weights0, unsigned int* barrier, ConvParams p,
                         cudaStream_t st);

@@ -100,6 +100,27 @@ def test_dncnn_forward_against_fp32_oracle(nets):
         assert (got - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 256, 256), (1, 3, 64, 64), (2, 3, 100, 200), (1, 3, 37, 150), (1, 3, 5, 17), (1, 3, 1, 1),
+                                   (3, 3, 70, 256), (1, 3, 3, 130), (1, 3, 64, 300), (4, 3, 256, 256)])
+@pytest.mark.parametrize("depth", [20, 5])
+def test_fused_layer_pairs_equal_single_layers(shape, depth, monkeypatch):
+    """Few chains: two hidden layers per launch (conv_fused2.cu, the intermediate rows stay in shared memory, the strips' edge pixels
+    cross the CTA pair by st.async) must equal the per-layer launches BIT FOR BIT -- the intermediate is rounded to bf16 either
+    way.  Shapes: R = 4 / 2 / 1 row blocks, ragged strips, images smaller than a tile, an odd number of hidden layers
+    (depth 5: one pair + a single layer), and two shapes the fused path does not take (W > 256, more than one wave)."""
+    sd = P.random_dncnn_state_dict(7, depth, scale=2.0)
+    den = P.DnCNN(depth=depth, pretrained=sd)
+    x = torch.rand(*shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    monkeypatch.setenv("PSGLA_CONV_FUSE2", "0")
+    ref = den.forward(x, 2 / 255).clone()
+    monkeypatch.setenv("PSGLA_CONV_FUSE2", "1")
+    for _ in range(3):  # repeated: the launches overlap their predecessors' tails (PDL), a race would not repeat bit for bit
+        got = den.forward(x, 2 / 255)
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), (got - ref).abs().max().item()
+    assert torch.isfinite(ref).all() and (ref - x).abs().max().item() > 1e-3
+
+
 def test_blur_against_reference_formulation():
     torch.manual_seed(0)
     im = torch.rand(2, 3, 45, 70, device="cuda")
