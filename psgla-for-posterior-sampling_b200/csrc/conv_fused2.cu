@@ -56,7 +56,12 @@ struct ConvF2Cfg {
 struct F2Params {
   const uint8_t* weights2;  // second layer: 9 taps, swizzled, all 64 output channels (as ConvParams::weights)
   const float* bias2;
+  long long* trace;  // PSGLA_F2_TRACE=1 (development): 64 clock64 stamps per CTA, see fused2_print_trace
 };
+#define F2_STAMP(k)                                                          \
+  do {                                                                       \
+    if (f.trace) f.trace[(size_t)blockIdx.x * 96 + (k)] = clock64();         \
+  } while (0)
 
 // 16 bytes into the shared memory of another CTA of the cluster; the bytes count as a transaction on that CTA's mbarrier
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t mbar_cluster_addr) {
@@ -92,33 +97,26 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   griddep_launch_dependents();
+  if (threadIdx.x == 0) F2_STAMP(0);
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < F2_NSTAGE; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 4);
+  // This prologue sits on every launch's critical path (one short item per CTA): one barrier per thread, nothing that waits
+  // for global memory (the biases are fetched by the epilogue warps behind the cluster barrier).
+  {
+    constexpr int N_BAR = 2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3 + F2_MID;
+    const int i = threadIdx.x;
+    if (i < N_BAR) {
+      uint32_t count = 1;                                                              // full, aempty, tfull, wbar, wready, done
+      if (i >= F2_NSTAGE && i < 2 * F2_NSTAGE) count = 4;                              // empty: four loader warps
+      else if (i >= 2 * F2_NSTAGE && i < 2 * F2_NSTAGE + TS_NA) count = 8;             // afull: loader warps of both CTAs
+      else if (i >= 2 * F2_NSTAGE + 2 * TS_NA + TS_NACC && i < 2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC) count = 8;  // tempty
+      else if (i >= N_BAR - F2_MID) count = 4;                                         // mfull: one epilogue group (+ 128 B from the peer)
+      mbar_init(&full[i], count);
+      fence_barrier_init();
     }
-    for (int i = 0; i < TS_NA; ++i) {
-      mbar_init(&afull[i], 8);
-      mbar_init(&aempty[i], 1);
-    }
-    for (int i = 0; i < TS_NACC; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
-    }
-    mbar_init(wbar, 1);
-    mbar_init(wready, 1);
-    mbar_init(done, 1);
-    for (int i = 0; i < F2_MID; ++i) mbar_init(&mfull[i], 4);
-    fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc2(tmem_ptr_s, 512);
     tmem_relinquish2();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * NOUT) {
-    const int i = threadIdx.x - 64;
-    bias_s[i] = i < NOUT ? p.bias[i] : f.bias2[i - NOUT];
   }
   if (threadIdx.x >= 192 && threadIdx.x < 192 + F2_MID * 8) {
     // the intermediate layer's zero padding left of strip 0 (box row 0) / right of strip 1 (box row 129)
@@ -129,6 +127,7 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   tc_fence_before();
   cluster_sync();  // barriers (and halo zeros) of both CTAs are in place before any remote arrive / store / multicast commit
   tc_fence_after();
+  if (threadIdx.x == 0) F2_STAMP(1);
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t afull_c = mapa_shared(smem_u32(afull), 0);
   const uint32_t tempty_c = mapa_shared(smem_u32(tempty), 0);
@@ -141,8 +140,26 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+      // ---------------------------------------------------------------- TMA producer (input rows; the weights are warp 1's)
       tma_prefetch_desc(&tmap);
+      griddep_wait();
+      F2_STAMP(2);
+      for (int q = 0; q < n_in; ++q) {
+        const uint32_t slot = (uint32_t)q % F2_NSTAGE;
+        mbar_wait(&empty[slot], (((uint32_t)q / F2_NSTAGE) & 1) ^ 1);
+        mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
+        tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, i_lo + q, c.b);
+        if (f.trace && q == F2_NSTAGE - 1)  // development: when the first rows land
+          for (int k = 0; k < F2_NSTAGE; ++k) {
+            mbar_wait(&full[k], 0);
+            F2_STAMP(58 + k);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both layers' weights (this CTA's 32 output channels of each): constant across launches, so no dependency wait; issued
+      // here because 18 bulk copies take ~1 800 cycles to ISSUE, which the input rows must not queue behind
       mbar_expect_tx(wbar, 2 * Cfg::W_BYTES);
       for (int t = 0; t < 9; ++t)
         bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES, Cfg::TAP_BYTES, wbar);
@@ -153,15 +170,8 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         mbar_wait(wbar, 0);
         mbar_arrive_cluster(mapa_shared(smem_u32(wready), 0));
       }
-      griddep_wait();
-      for (int q = 0; q < n_in; ++q) {
-        const uint32_t slot = (uint32_t)q % F2_NSTAGE;
-        mbar_wait(&empty[slot], (((uint32_t)q / F2_NSTAGE) & 1) ^ 1);
-        mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
-        tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, i_lo + q, c.b);
-      }
     }
-  } else if (warp == 1) {
+    __syncwarp();
     if (rank == 0) {
       // ---------------------------------------------------------------- MMA issuer of the pair
       // Rows enter tensor memory in ONE sequence q = 0 .. n_in + n_mid - 1 (input rows, then intermediate rows), slot q % 4.
@@ -171,56 +181,64 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       mbar_wait(wbar, 0);
       mbar_wait_cluster(wready, 0);
       tc_fence_after();
-      uint32_t T = 0;
-      int waited = 0;
+      if (lane == 0) F2_STAMP(3);
+      // ONE thread runs the whole issue loop, barrier waits included.  The tensor pipe's queue is shallow: whatever the issuing
+      // thread executes between two MMAs beyond a few dozen cycles is a bubble in the pipe (measured with the stamps below: one
+      // warp-uniform wait / elect / syncwarp boundary per dy group cost 180 cycles per 384 cycles of MMAs), so the loop carries
+      // nothing but try_waits that pass at once in steady state, address adds and the MMAs.
+      if (elect_one()) {
+        uint32_t T = 0;
+        int waited = 0;
 #pragma unroll 1
-      for (int ph = 0; ph < 2; ++ph) {
-        // phase ph: output rows [o_lo, o_hi] of the phase from source rows [s_lo, s_hi], which sit at sequence q0 + (row - s_lo)
-        const int o_lo = ph ? c.y0 : m_lo, o_hi = ph ? c.y0 + c.rcur - 1 : m_hi;
-        const int s_lo = ph ? m_lo : i_lo, s_hi = ph ? m_hi : i_hi;
-        const int q0 = ph ? n_in : 0;
-        const uint32_t wl = w_lo + (uint32_t)(ph * (Cfg::W_BYTES >> 4));
-        for (int y = o_lo; y <= o_hi; ++y, ++T) {
-          const int need = q0 + min(y + 1, s_hi) - s_lo + 1;
-          while (waited < need) {
-            mbar_wait(&afull[waited % TS_NA], ((uint32_t)waited / TS_NA) & 1);
-            ++waited;
-          }
-          const uint32_t acc = T % TS_NACC;
-          mbar_wait(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * NOUT;
-          if (elect_one()) {
+        for (int ph = 0; ph < 2; ++ph) {
+          // phase ph: output rows [o_lo, o_hi] of the phase from source rows [s_lo, s_hi], which sit at sequence q0 + (row - s_lo)
+          const int o_lo = ph ? c.y0 : m_lo, o_hi = ph ? c.y0 + c.rcur - 1 : m_hi;
+          const int s_lo = ph ? m_lo : i_lo;
+          const int q0 = ph ? n_in : 0;
+          const uint32_t wl = w_lo + (uint32_t)(ph * (Cfg::W_BYTES >> 4));
+#pragma unroll 1
+          for (int y = o_lo; y <= o_hi; ++y, ++T) {
+            const uint32_t acc = T % TS_NACC;
+            mbar_wait_spin(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
+            const uint32_t d_tmem = tmem_base + acc * NOUT;
             uint32_t accumulate = 0;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int yy = y + dy - 1;
               if (yy < 0 || yy >= p.H) continue;  // the layer's zero padding above / below the image
-              const uint32_t q = (uint32_t)(q0 + yy - s_lo);
-              const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
+              // a source row is awaited right before the first 12 MMAs that read it: at the start of a phase the MMAs of the
+              // first rows run while the loader warps are still copying the next one
+              const int q = q0 + yy - s_lo;
+              if (q == waited) {
+                mbar_wait_spin(&afull[(uint32_t)q % TS_NA], ((uint32_t)q / TS_NA) & 1);
+                ++waited;
+              }
+              tc_fence_after();
+              const uint32_t a_t = tmem_base + TS_A_COL0 + ((uint32_t)q % TS_NA) * 96u;
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t bl = wl + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
-                  umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
-                  accumulate = 1;
+                  umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate | (uint32_t)(dx | k));
                 }
               }
-              // source row y - 1 is dead once these 12 MMAs retire
-              if (dy == 0 && y - 1 >= s_lo) umma_commit2(&aempty[(uint32_t)(q0 + y - 1 - s_lo) % TS_NA], 3);
+              accumulate = 1;
+              // source row y - 1 is dead once these 12 MMAs retire; after the phase's last output row so are the others
+              if ((dy == 0 && y - 1 >= s_lo) || y == o_hi) umma_commit2(&aempty[(uint32_t)q % TS_NA], 3);
+              if (y == o_lo && dy == 2) F2_STAMP(ph ? 8 : 5);
             }
             umma_commit2(&tfull[acc], 3);
-            if (y == o_hi)
-              for (int yy = y; yy <= s_hi; ++yy) umma_commit2(&aempty[(uint32_t)(q0 + yy - s_lo) % TS_NA], 3);
+            F2_STAMP(48 + T);
           }
-          __syncwarp();
         }
+        umma_commit2(done, 3);
       }
-      if (elect_one()) umma_commit2(done, 3);
       __syncwarp();
     }
-    mbar_wait(done, 0);  // both CTAs: no MMA still reads this CTA's shared / tensor memory, no commit is still in flight
+    mbar_wait(done, 0);
+    if (lane == 0) F2_STAMP(9);
+    // both CTAs: no MMA still reads this CTA's shared / tensor memory, no commit is still in flight
   } else if (warp < 6) {
     // ---------------------------------------------------------------- loaders: TMA ring / mid ring -> registers -> TMEM
     const int q4 = warp & 3;
@@ -232,34 +250,48 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       const uint32_t as = (uint32_t)q % TS_NA;
       uint32_t tile;
       uint32_t slot = 0;
+      const bool fine = q == 1 && warp == 2 && lane == 0;
+      if (fine) F2_STAMP(64);
       if (q < n_in) {
         slot = (uint32_t)q % F2_NSTAGE;
         mbar_wait(&full[slot], ((uint32_t)q / F2_NSTAGE) & 1);
+        if (q == 0 && warp == 2 && lane == 0) F2_STAMP(4);
         tile = ring_addr + slot * Cfg::SLOT_BYTES;
       } else {
         mbar_wait(&mfull[q - n_in], 0);
         tile = mid_addr + (uint32_t)(q - n_in) * Cfg::MID_SLOT;
       }
+      if (fine) F2_STAMP(65);
       mbar_wait(&aempty[as], (((uint32_t)q / TS_NA) & 1) ^ 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) F2_STAMP(32 + q);
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         uint32_t v[32];
         ld_swizzled_row128(tile, m + dx, v);
         tmem_st_32x32b_x32(lane_taddr + as * 96u + dx * 32u, v);
       }
+      if (fine) F2_STAMP(66);
       tmem_st_wait();
+      if (fine) F2_STAMP(67);
       tc_fence_before();
       __syncwarp();
+      if (fine) F2_STAMP(68);
       if (lane == 0) {
         if (q < n_in) mbar_arrive(&empty[slot]);
         mbar_arrive_remote(afull_c + as * 8u);
+        if (warp == 2) F2_STAMP(16 + q);
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
     const int ew = warp - 6;
     const int grp = ew >> 2, q4 = warp & 3;
+    {
+      const int i = ew * 32 + lane;
+      if (i < 2 * NOUT) bias_s[i] = i < NOUT ? p.bias[i] : f.bias2[i - NOUT];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // the eight epilogue warps only
+    }
     // phase 1: layer l -> the mid ring (this CTA's 128 pixels, plus its edge pixel into the peer's ring)
     {
       const int mpx = q4 * 32 + lane;       // pixel of the strip
@@ -278,6 +310,7 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const uint32_t acc = (uint32_t)t % TS_NACC;
         mbar_wait(&tfull[acc], ((uint32_t)t / TS_NACC) & 1);
         tc_fence_after();
+        if (q4 == 0 && lane == 0 && (t == 0 || t == n_mid - 1)) F2_STAMP(t == 0 ? 6 : 7);
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
         uint32_t v[NOUT];
 #pragma unroll
@@ -312,9 +345,12 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t T = (uint32_t)n_mid;
     epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, ring + ew * Cfg::STAGE_BYTES, bias_s + NOUT, tfull, tempty, tmem_base, grp, q4, lane,
                                    T, tempty_c, 1);
+    if (q4 == 0 && lane == 0) F2_STAMP(10 + grp);
   }
   tc_fence_before();
-  cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still signal, read or write it
+  cluster_sync();
+  if (threadIdx.x == 0) F2_STAMP(12);
+  // neither CTA may exit (or free tensor memory) while its partner can still signal, read or write it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
@@ -382,7 +418,14 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   p.strips = 2;
   p.row_blocks = (H + R - 1) / R;
   p.n_items = B * 2 * p.row_blocks;
-  F2Params f{w2, b2};
+  F2Params f{w2, b2, nullptr};
+  static long long* trace_dev = nullptr;
+  const bool trace = getenv("PSGLA_F2_TRACE") != nullptr;
+  if (trace) {
+    if (!trace_dev) PSGLA_CUDA_TRY(cudaMalloc(&trace_dev, 512 * 96 * sizeof(long long)));
+    PSGLA_CUDA_TRY(cudaMemsetAsync(trace_dev, 0, 512 * 96 * sizeof(long long), st));
+    if (p.n_items <= 512) f.trace = trace_dev;
+  }
   CUtensorMap map, map_out;
   rc = get_act_tensor_map(&map, in, B, H, W, 64, BOX_W);
   if (rc) return rc;
@@ -404,6 +447,31 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   cfg.numAttrs = 2;
   PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused2_kernel, map, map_out, p, f));
   *applicable = 1;
+  if (f.trace) {
+    // clock64 stamps (cycles after the CTA's entry): 1 prologue + cluster sync done, 2 previous grid complete, 3 weights of both
+    // CTAs landed, 4 first input row landed, 5 / 8 first MMA of phase 1 / 2 may issue, 6 / 7 first / last intermediate row's
+    // accumulator complete, 9 all MMAs complete, 10 / 11 epilogue groups done (stores complete), 12 final cluster sync
+    static long long host[512 * 96];
+    PSGLA_CUDA_TRY(cudaStreamSynchronize(st));
+    PSGLA_CUDA_TRY(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    const int ctas[] = {0, 1, p.n_items / 2, p.n_items - 2};
+    for (int cta : ctas) {
+      fprintf(stderr, "f2 trace cta %3d:", cta);
+      for (int k = 1; k <= 12; ++k) fprintf(stderr, " %d:%lld", k, host[cta * 96 + k] ? host[cta * 96 + k] - host[cta * 96] : -1);
+      fprintf(stderr, "\n   loader pass start/end per row:");
+      for (int k = 0; k < 14; ++k)
+        if (host[cta * 96 + 16 + k]) fprintf(stderr, " %lld-%lld", host[cta * 96 + 32 + k] - host[cta * 96], host[cta * 96 + 16 + k] - host[cta * 96]);
+      fprintf(stderr, "\n   first rows landed: %lld %lld %lld", host[cta * 96 + 58] - host[cta * 96], host[cta * 96 + 59] - host[cta * 96],
+              host[cta * 96 + 60] - host[cta * 96]);
+      fprintf(stderr, "\n   loader pass of row 1: top %lld, row landed %lld, stores issued %lld, wait::st done %lld, syncwarp done %lld",
+              host[cta * 96 + 64] - host[cta * 96], host[cta * 96 + 65] - host[cta * 96], host[cta * 96 + 66] - host[cta * 96],
+              host[cta * 96 + 67] - host[cta * 96], host[cta * 96 + 68] - host[cta * 96]);
+      fprintf(stderr, "\n   issuer, output row issued:");
+      for (int k = 0; k < 10; ++k)
+        if (host[cta * 96 + 48 + k]) fprintf(stderr, " %lld", host[cta * 96 + 48 + k] - host[cta * 96]);
+      fprintf(stderr, "\n");
+    }
+  }
   return PSGLA_OK;
 }
 

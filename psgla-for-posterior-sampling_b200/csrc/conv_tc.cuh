@@ -214,7 +214,10 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
       }
     }
   }
-  if (lane == 0) bulk_wait_group0();
+  // Before the CTA exits its stores must have READ their staging boxes; their writes are complete and visible when the grid
+  // completes, which is what a dependent launch's griddepcontrol.wait awaits.  (A kernel that publishes its rows to other CTAs
+  // of the same grid must wait for the writes itself: experiments.cu.)
+  if (lane == 0) bulk_wait_group_read0();
 }
 
 // The same with the first residual tensor fetched by TMA (pair kernel, DRUNet's 64-channel residual blocks).  At 64 chains of
@@ -349,7 +352,7 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
     ++n;
     it = nxt;
   }
-  if (lane == 0) bulk_wait_group0();
+  if (lane == 0) bulk_wait_group_read0();  // see epilogue_hidden
 }
 
 // Last layer: the fused Langevin "post" step, fp32 NCHW (restoration_algorithms.py:238-262 / :115-135), optionally followed

@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Unbounded form for the MMA-issuing thread only, whose loop must stay a handful of instructions (anything it executes between
+// two MMAs is a bubble in the tensor pipe); a protocol bug still surfaces through the bounded waits of the other warps.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
 // ------------------------------------------------------------------ thread-block clusters (CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -321,6 +328,16 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+// shared memory -> TMEM without registers: 128 rows x 256 bit (one K16 bf16 slice of an A operand, 8 columns) from the matrix the
+// descriptor names (same descriptor format and swizzle handling as an MMA operand); asynchronous, ordered with the
+// tcgen05.mma / tcgen05.cp / tcgen05.commit that the same thread issues afterwards.  cta_group::2: each CTA of the pair
+// copies from its own shared memory (same offsets) into its own tensor memory.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void tmem_cp2_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t saddr) {
