@@ -11,7 +11,8 @@
 //            the very layout a TMA row box has (130 pixels x 128 B, 16-byte chunk j of box row r at j ^ (r & 7)); the one
 //            pixel a strip needs from its neighbour (box row 0 / 129) is written into the PEER's ring by st.async
 //            (shared::cluster, completes transaction bytes on the peer's "row ready" mbarrier, so no fence is needed);
-//   phase 2: layer l + 1 for rows y0 .. y0 + R - 1, the loader warps reading the mid ring instead of the TMA ring.
+//   phase 2: layer l + 1 for rows y0 .. y0 + R - 1, the loader warps reading the mid ring instead of the TMA ring; the epilogue
+//            stores straight from registers (one pixel = 128 contiguous bytes per lane).
 // The intermediate activations are rounded to bf16 exactly as when they travel through global memory, so the result is
 // bit-identical to two conv3x3_ts2_kernel launches (tests/test_image_gpu.py::test_fused_layer_pairs_equal_single_layers).
 // Limits: W <= 256 (the pair holds whole rows, so every halo pixel is on chip) and a single wave of pairs; everything else
@@ -45,17 +46,15 @@ struct ConvF2Cfg {
   static constexpr int OFF_BAR = OFF_BIAS + 512;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
-  // phase 2's output staging boxes (one 32-pixel box per epilogue warp) reuse the TMA ring, which is dead by then
-  static constexpr int STAGE_BYTES = 32 * 64 * 2;
   static_assert(OFF_RING % 1024 == 0 && W_BYTES % 1024 == 0, "UMMA / TMA operands need 1 KB aligned bases");
-  static_assert(EPI_WARPS * STAGE_BYTES <= F2_NSTAGE * SLOT_BYTES, "staging boxes do not fit the TMA ring");
-  static_assert((2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3 + F2_MID) * 8 + 4 <= BAR_BYTES, "barrier block overflows");
+  static_assert((2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 5 + F2_MID) * 8 + 4 <= BAR_BYTES, "barrier block overflows");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
 struct F2Params {
   const uint8_t* weights2;  // second layer: 9 taps, swizzled, all 64 output channels (as ConvParams::weights)
   const float* bias2;
+  __nv_bfloat16* out;  // bf16 NHWC [B][H][W][64]
   long long* trace;  // PSGLA_F2_TRACE=1 (development): 64 clock64 stamps per CTA, see fused2_print_trace
 };
 #define F2_STAMP(k)                                                          \
@@ -71,8 +70,7 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& 
 }
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
-conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p,
-                      const F2Params f) {
+conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const F2Params f) {
   using Cfg = ConvF2Cfg;
   constexpr int NOUT = 64;
   extern __shared__ uint8_t smem_raw[];
@@ -90,7 +88,9 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   uint64_t* wbar = tempty + TS_NACC;                                  // local: this CTA's halves of both layers' weights landed
   uint64_t* wready = wbar + 1;                                        // leader: the peer's landed
   uint64_t* done = wready + 1;                                        // both (multicast): every MMA of the launch completed
-  uint64_t* mfull = done + 1;                                         // local: an intermediate row is complete (4 warps + 128 B from the peer)
+  uint64_t* wbar2 = done + 1;                                         // local: the second layer's weights landed
+  uint64_t* wready2 = wbar2 + 1;                                      // leader: the peer's second layer landed
+  uint64_t* mfull = wready2 + 1;                                         // local: an intermediate row is complete (4 warps + 128 B from the peer)
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(mfull + F2_MID);
 
   const int warp = threadIdx.x >> 5;
@@ -99,76 +99,139 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   griddep_launch_dependents();
   if (threadIdx.x == 0) F2_STAMP(0);
 
-  // This prologue sits on every launch's critical path (one short item per CTA): one barrier per thread, nothing that waits
-  // for global memory (the biases are fetched by the epilogue warps behind the cluster barrier).
-  {
-    constexpr int N_BAR = 2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC + 3 + F2_MID;
-    const int i = threadIdx.x;
-    if (i < N_BAR) {
-      uint32_t count = 1;                                                              // full, aempty, tfull, wbar, wready, done
-      if (i >= F2_NSTAGE && i < 2 * F2_NSTAGE) count = 4;                              // empty: four loader warps
-      else if (i >= 2 * F2_NSTAGE && i < 2 * F2_NSTAGE + TS_NA) count = 8;             // afull: loader warps of both CTAs
-      else if (i >= 2 * F2_NSTAGE + 2 * TS_NA + TS_NACC && i < 2 * F2_NSTAGE + 2 * TS_NA + 2 * TS_NACC) count = 8;  // tempty
-      else if (i >= N_BAR - F2_MID) count = 4;                                         // mfull: one epilogue group (+ 128 B from the peer)
-      mbar_init(&full[i], count);
-      fence_barrier_init();
-    }
-  }
-  if (warp == 1) {
-    tmem_alloc2(tmem_ptr_s, 512);
-    tmem_relinquish2();
-  }
-  if (threadIdx.x >= 192 && threadIdx.x < 192 + F2_MID * 8) {
-    // the intermediate layer's zero padding left of strip 0 (box row 0) / right of strip 1 (box row 129)
-    const int i = threadIdx.x - 192;
-    const uint32_t a = smem_u32(mid) + (uint32_t)(i >> 3) * Cfg::MID_SLOT + (rank == 0 ? 0u : 129u * 128u) + (uint32_t)(i & 7) * 16u;
-    st_shared_v4(a, make_uint4(0u, 0u, 0u, 0u));
-  }
-  tc_fence_before();
-  cluster_sync();  // barriers (and halo zeros) of both CTAs are in place before any remote arrive / store / multicast commit
-  tc_fence_after();
-  if (threadIdx.x == 0) F2_STAMP(1);
-  const uint32_t tmem_base = *tmem_ptr_s;
-  const uint32_t afull_c = mapa_shared(smem_u32(afull), 0);
-  const uint32_t tempty_c = mapa_shared(smem_u32(tempty), 0);
-
   // the pair's work item: output rows [y0, y0 + rcur), intermediate rows [m_lo, m_hi], input rows [i_lo, i_hi]
   const ItemCoord c = decode_item(p, blockIdx.x);
   const int m_lo = c.ylo, m_hi = c.yhi;
   const int i_lo = max(m_lo - 1, 0), i_hi = min(m_hi + 1, p.H - 1);
   const int n_in = i_hi - i_lo + 1, n_mid = m_hi - m_lo + 1;
 
+  // The prologue sits on every launch's critical path (one short item per CTA), so whatever can start before the cluster
+  // barrier does: the producer initialises its own "row landed" barriers, waits for the previous grid and issues the first
+  // rows' loads; warp 1's lane 0 does the same for the weights; the other barriers are initialised one per thread.
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer (input rows; the weights are warp 1's)
       tma_prefetch_desc(&tmap);
+      for (int i = 0; i < F2_NSTAGE; ++i) mbar_init(&full[i], 1);
+      fence_barrier_init();
+      fence_proxy_async();
       griddep_wait();
       F2_STAMP(2);
-      for (int q = 0; q < n_in; ++q) {
+      for (int q = 0; q < min(n_in, F2_NSTAGE); ++q) {
+        mbar_expect_tx(&full[q], Cfg::BOX_BYTES);
+        tma_load_4d(ring + q * Cfg::SLOT_BYTES, &tmap, &full[q], 0, c.x0 - 1, i_lo + q, c.b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    tmem_alloc2(tmem_ptr_s, 512);
+    tmem_relinquish2();
+    if (lane == 0) {
+      // The weights (this CTA's 32 output channels of each layer) are constant across launches: no dependency wait.  The SM's
+      // TMA queue is served in order and a bulk copy takes ~100 cycles to issue, so: the first layer's weights from here,
+      // ahead of the input rows (the first MMA needs both); the second layer's behind the rows, below.
+      mbar_init(wbar, 1);
+      mbar_init(wbar2, 1);
+      mbar_init(wready, 1);
+      mbar_init(wready2, 1);
+      mbar_init(done, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+      mbar_expect_tx(wbar, Cfg::W_BYTES);
+      for (int t = 0; t < 9; ++t)
+        bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES, Cfg::TAP_BYTES, wbar);
+    }
+    __syncwarp();
+  } else {
+    // empty (4: the loader warps), afull (8: the loader warps of both CTAs), aempty, tfull (1), tempty (8), mfull (4: one
+    // epilogue group, + 128 B from the peer)
+    constexpr int N0 = F2_NSTAGE, N1 = N0 + TS_NA, N2 = N1 + TS_NA, N3 = N2 + TS_NACC, N4 = N3 + TS_NACC, N5 = N4 + F2_MID;
+    const int i = threadIdx.x - 64;
+    if (i < N5) {
+      uint64_t* bar = i < N0 ? &empty[i] : i < N1 ? &afull[i - N0] : i < N2 ? &aempty[i - N1] : i < N3 ? &tfull[i - N2]
+                      : i < N4 ? &tempty[i - N3] : &mfull[i - N4];
+      const uint32_t count = i < N0 ? 4u : i < N1 ? 8u : i < N3 ? 1u : i < N4 ? 8u : 4u;
+      mbar_init(bar, count);
+      fence_barrier_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();        // this CTA: barriers, the TMEM base address
+  cluster_sync_relaxed();  // the pair: both CTAs' barriers exist before any remote arrive / store / multicast commit
+  tc_fence_after();
+  if (threadIdx.x == 0) F2_STAMP(1);
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t afull_c = mapa_shared(smem_u32(afull), 0);
+  const uint32_t tempty_c = mapa_shared(smem_u32(tempty), 0);
+
+  // One loader pass: row q of the sequence (input rows, then intermediate rows) from its ring into TMEM slot q % 4, three times,
+  // shifted by dx = 0, 1, 2 pixels; run by four warps that cover the four TMEM lane quarters.  A pass is ~500 cycles of
+  // shared-memory reads and TMEM stores plus four mbarrier operations of ~90 cycles, and passes of one warp set are serial; so
+  // where rows wait in line on the critical path -- the first three rows of the launch, the rows the second layer starts
+  // with -- the epilogue groups, idle at those moments, each take one (helper_row) and the passes run side by side.
+  auto loader_pass = [&](int q, int q4, int lane_, bool stamp) {
+    const int m = q4 * 32 + lane_;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TS_A_COL0;
+    const uint32_t as = (uint32_t)q % TS_NA;
+    uint32_t tile;
+    uint32_t slot = 0;
+    if (q < n_in) {
+      slot = (uint32_t)q % F2_NSTAGE;
+      mbar_wait(&full[slot], ((uint32_t)q / F2_NSTAGE) & 1);
+      if (q == 0 && stamp) F2_STAMP(4);
+      tile = smem_u32(ring) + slot * Cfg::SLOT_BYTES;
+    } else {
+      mbar_wait(&mfull[q - n_in], 0);
+      tile = smem_u32(mid) + (uint32_t)(q - n_in) * Cfg::MID_SLOT;
+    }
+    mbar_wait(&aempty[as], (((uint32_t)q / TS_NA) & 1) ^ 1);
+    tc_fence_after();
+    if (stamp) F2_STAMP(32 + q);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      uint32_t v[32];
+      ld_swizzled_row128(tile, m + dx, v);
+      tmem_st_32x32b_x32(lane_taddr + as * 96u + dx * 32u, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane_ == 0) {
+      if (q < n_in) mbar_arrive(&empty[slot]);
+      mbar_arrive_remote(afull_c + as * 8u);
+      if (stamp) F2_STAMP(16 + q);
+    }
+  };
+  // rows taken by an epilogue group: input rows 1 and 2 (groups 0 and 1, before their first accumulator), and the third
+  // intermediate row (the group that is NOT draining the last intermediate row's accumulator; it also owns the second layer's
+  // first output row, which cannot start before that pass anyway)
+  auto helper_row = [&](int q) { return ((q == 1 || q == 2) && q < n_in) || (n_mid > 2 && q == n_in + 2); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer: the rows beyond the first three
+      if (f.trace)  // development: when the first rows land
+        for (int k = 0; k < min(n_in, F2_NSTAGE); ++k) {
+          mbar_wait(&full[k], 0);
+          F2_STAMP(58 + k);
+        }
+      for (int q = F2_NSTAGE; q < n_in; ++q) {
         const uint32_t slot = (uint32_t)q % F2_NSTAGE;
         mbar_wait(&empty[slot], (((uint32_t)q / F2_NSTAGE) & 1) ^ 1);
         mbar_expect_tx(&full[slot], Cfg::BOX_BYTES);
         tma_load_4d(ring + slot * Cfg::SLOT_BYTES, &tmap, &full[slot], 0, c.x0 - 1, i_lo + q, c.b);
-        if (f.trace && q == F2_NSTAGE - 1)  // development: when the first rows land
-          for (int k = 0; k < F2_NSTAGE; ++k) {
-            mbar_wait(&full[k], 0);
-            F2_STAMP(58 + k);
-          }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // both layers' weights (this CTA's 32 output channels of each): constant across launches, so no dependency wait; issued
-      // here because 18 bulk copies take ~1 800 cycles to ISSUE, which the input rows must not queue behind
-      mbar_expect_tx(wbar, 2 * Cfg::W_BYTES);
-      for (int t = 0; t < 9; ++t)
-        bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES, Cfg::TAP_BYTES, wbar);
+      mbar_expect_tx(wbar2, Cfg::W_BYTES);
       for (int t = 0; t < 9; ++t)
         bulk_load(smem_w + Cfg::W_BYTES + t * Cfg::TAP_BYTES, f.weights2 + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES,
-                  Cfg::TAP_BYTES, wbar);
-      if (rank != 0) {
+                  Cfg::TAP_BYTES, wbar2);
+      if (rank != 0) {  // tell the leader (behind the cluster barrier: its barrier exists), once per layer
         mbar_wait(wbar, 0);
         mbar_arrive_cluster(mapa_shared(smem_u32(wready), 0));
+        mbar_wait(wbar2, 0);
+        mbar_arrive_cluster(mapa_shared(smem_u32(wready2), 0));
       }
     }
     __syncwarp();
@@ -196,6 +259,10 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
           const int s_lo = ph ? m_lo : i_lo;
           const int q0 = ph ? n_in : 0;
           const uint32_t wl = w_lo + (uint32_t)(ph * (Cfg::W_BYTES >> 4));
+          if (ph) {  // the second layer's weights: both CTAs' halves (they landed long ago)
+            mbar_wait_spin(wbar2, 0);
+            mbar_wait_cluster(wready2, 0);
+          }
 #pragma unroll 1
           for (int y = o_lo; y <= o_hi; ++y, ++T) {
             const uint32_t acc = T % TS_NACC;
@@ -241,48 +308,9 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // both CTAs: no MMA still reads this CTA's shared / tensor memory, no commit is still in flight
   } else if (warp < 6) {
     // ---------------------------------------------------------------- loaders: TMA ring / mid ring -> registers -> TMEM
-    const int q4 = warp & 3;
-    const int m = q4 * 32 + lane;
-    const uint32_t ring_addr = smem_u32(ring), mid_addr = smem_u32(mid);
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + TS_A_COL0;
     const int n_rows = n_in + n_mid;
-    for (int q = 0; q < n_rows; ++q) {
-      const uint32_t as = (uint32_t)q % TS_NA;
-      uint32_t tile;
-      uint32_t slot = 0;
-      const bool fine = q == 1 && warp == 2 && lane == 0;
-      if (fine) F2_STAMP(64);
-      if (q < n_in) {
-        slot = (uint32_t)q % F2_NSTAGE;
-        mbar_wait(&full[slot], ((uint32_t)q / F2_NSTAGE) & 1);
-        if (q == 0 && warp == 2 && lane == 0) F2_STAMP(4);
-        tile = ring_addr + slot * Cfg::SLOT_BYTES;
-      } else {
-        mbar_wait(&mfull[q - n_in], 0);
-        tile = mid_addr + (uint32_t)(q - n_in) * Cfg::MID_SLOT;
-      }
-      if (fine) F2_STAMP(65);
-      mbar_wait(&aempty[as], (((uint32_t)q / TS_NA) & 1) ^ 1);
-      tc_fence_after();
-      if (warp == 2 && lane == 0) F2_STAMP(32 + q);
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        uint32_t v[32];
-        ld_swizzled_row128(tile, m + dx, v);
-        tmem_st_32x32b_x32(lane_taddr + as * 96u + dx * 32u, v);
-      }
-      if (fine) F2_STAMP(66);
-      tmem_st_wait();
-      if (fine) F2_STAMP(67);
-      tc_fence_before();
-      __syncwarp();
-      if (fine) F2_STAMP(68);
-      if (lane == 0) {
-        if (q < n_in) mbar_arrive(&empty[slot]);
-        mbar_arrive_remote(afull_c + as * 8u);
-        if (warp == 2) F2_STAMP(16 + q);
-      }
-    }
+    for (int q = 0; q < n_rows; ++q)
+      if (!helper_row(q)) loader_pass(q, warp & 3, lane, warp == 2 && lane == 0);
   } else {
     // ---------------------------------------------------------------- epilogue: 2 groups x 4 warps
     const int ew = warp - 6;
@@ -292,6 +320,7 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       if (i < 2 * NOUT) bias_s[i] = i < NOUT ? p.bias[i] : f.bias2[i - NOUT];
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // the eight epilogue warps only
     }
+    if (1 + grp < n_in) loader_pass(1 + grp, q4, lane, q4 == 0 && lane == 0);
     // phase 1: layer l -> the mid ring (this CTA's 128 pixels, plus its edge pixel into the peer's ring)
     {
       const int mpx = q4 * 32 + lane;       // pixel of the strip
@@ -304,6 +333,10 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       const uint32_t peer_mid = mapa_shared(mid_addr, peer);
       const uint32_t peer_mfull = mapa_shared(smem_u32(mfull), peer);
       const bool edge = rank == 0 ? (mpx == TILE_M - 1) : (mpx == 0);
+      // the intermediate layer's zero padding left of strip 0 (box row 0) / right of strip 1 (box row 129): written by the lane
+      // whose own pixel is next to it, ahead of the same "row ready" arrive
+      const bool pad = rank == 0 ? (mpx == 0) : (mpx == TILE_M - 1);
+      const uint32_t r_pad = rank == 0 ? 0u : (uint32_t)(BOX_W - 1);
       const uint32_t r_peer = rank == 0 ? 0u : (uint32_t)(BOX_W - 1);  // where the peer's box holds that pixel
       for (int t = 0; t < n_mid; ++t) {
         if ((t & 1) != grp) continue;
@@ -331,6 +364,7 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
           if (!inside) o = make_uint4(0u, 0u, 0u, 0u);  // beyond the image: the next layer's zero padding
           st_shared_v4(row_addr + ((uint32_t)(j ^ (int)(r & 7u)) << 4), o);
           if (edge) st_async_v4(peer_row + ((uint32_t)(j ^ (int)(r_peer & 7u)) << 4), o, peer_mfull + (uint32_t)t * 8u);
+          if (pad) st_shared_v4(mid_addr + (uint32_t)t * Cfg::MID_SLOT + r_pad * 128u + ((uint32_t)j << 4), make_uint4(0u, 0u, 0u, 0u));
         }
         __syncwarp();
         if (lane == 0) {
@@ -341,14 +375,48 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         }
       }
     }
-    // phase 2: layer l + 1 -> staging box -> TMA store, as in the per-layer kernel; T continues after the intermediate rows
-    uint32_t T = (uint32_t)n_mid;
-    epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, ring + ew * Cfg::STAGE_BYTES, bias_s + NOUT, tfull, tempty, tmem_base, grp, q4, lane,
-                                   T, tempty_c, 1);
+    if (n_mid > 2 && grp == (n_mid & 1)) loader_pass(n_in + 2, q4, lane, q4 == 0 && lane == 0);
+    // phase 2: layer l + 1 -> registers -> global memory, one pixel (128 contiguous bytes) per lane.  No staging box and no TMA
+    // store here: with one item per CTA nothing overlaps the store's shared-memory round trip, and plain stores let the CTA
+    // retire as soon as they are issued (they are complete when the grid is, which is what the next launch waits for).
+    {
+      const int x = c.x0 + q4 * 32 + lane;
+      const bool relu = p.relu != 0;
+      const float4* bias4 = reinterpret_cast<const float4*>(bias_s + NOUT);
+      uint32_t T = (uint32_t)n_mid;  // accumulator stages and phases continue after the intermediate rows
+      for (int y = c.y0; y < c.y0 + c.rcur; ++y, ++T) {
+        if ((int)(T & 1) != grp) continue;
+        const uint32_t acc = T % TS_NACC;
+        mbar_wait(&tfull[acc], (T / TS_NACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * NOUT;
+        uint32_t v[NOUT];
+#pragma unroll
+        for (int h = 0; h < NOUT / 32; ++h) tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_remote(tempty_c + acc * 8u);
+        __nv_bfloat16* dst = f.out + (((size_t)c.b * p.H + y) * p.W + x) * NOUT;
+#pragma unroll
+        for (int j = 0; j < NOUT / 8; j += 2) {
+          uint4 o[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 b0 = bias4[2 * (j + h)], b1 = bias4[2 * (j + h) + 1];
+            const int e = 8 * (j + h);
+            o[h].x = pack_bf16x2(__uint_as_float(v[e + 0]) + b0.x, __uint_as_float(v[e + 1]) + b0.y, relu);
+            o[h].y = pack_bf16x2(__uint_as_float(v[e + 2]) + b0.z, __uint_as_float(v[e + 3]) + b0.w, relu);
+            o[h].z = pack_bf16x2(__uint_as_float(v[e + 4]) + b1.x, __uint_as_float(v[e + 5]) + b1.y, relu);
+            o[h].w = pack_bf16x2(__uint_as_float(v[e + 6]) + b1.z, __uint_as_float(v[e + 7]) + b1.w, relu);
+          }
+          if (x < p.W) stg256(dst + 8 * j, o[0], o[1]);
+        }
+      }
+    }
     if (q4 == 0 && lane == 0) F2_STAMP(10 + grp);
   }
   tc_fence_before();
-  cluster_sync();
+  cluster_sync_relaxed();
   if (threadIdx.x == 0) F2_STAMP(12);
   // neither CTA may exit (or free tensor memory) while its partner can still signal, read or write it
   if (warp == 1) {
@@ -418,7 +486,7 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   p.strips = 2;
   p.row_blocks = (H + R - 1) / R;
   p.n_items = B * 2 * p.row_blocks;
-  F2Params f{w2, b2, nullptr};
+  F2Params f{w2, b2, (__nv_bfloat16*)out, nullptr};
   static long long* trace_dev = nullptr;
   const bool trace = getenv("PSGLA_F2_TRACE") != nullptr;
   if (trace) {
@@ -426,10 +494,8 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
     PSGLA_CUDA_TRY(cudaMemsetAsync(trace_dev, 0, 512 * 96 * sizeof(long long), st));
     if (p.n_items <= 512) f.trace = trace_dev;
   }
-  CUtensorMap map, map_out;
+  CUtensorMap map;
   rc = get_act_tensor_map(&map, in, B, H, W, 64, BOX_W);
-  if (rc) return rc;
-  rc = get_act_tensor_map(&map_out, out, B, H, W, 64, 32);
   if (rc) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)p.n_items);
@@ -445,7 +511,7 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused2_kernel, map, map_out, p, f));
+  PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused2_kernel, map, p, f));
   *applicable = 1;
   if (f.trace) {
     // clock64 stamps (cycles after the CTA's entry): 1 prologue + cluster sync done, 2 previous grid complete, 3 weights of both
@@ -463,9 +529,6 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
         if (host[cta * 96 + 16 + k]) fprintf(stderr, " %lld-%lld", host[cta * 96 + 32 + k] - host[cta * 96], host[cta * 96 + 16 + k] - host[cta * 96]);
       fprintf(stderr, "\n   first rows landed: %lld %lld %lld", host[cta * 96 + 58] - host[cta * 96], host[cta * 96 + 59] - host[cta * 96],
               host[cta * 96 + 60] - host[cta * 96]);
-      fprintf(stderr, "\n   loader pass of row 1: top %lld, row landed %lld, stores issued %lld, wait::st done %lld, syncwarp done %lld",
-              host[cta * 96 + 64] - host[cta * 96], host[cta * 96 + 65] - host[cta * 96], host[cta * 96 + 66] - host[cta * 96],
-              host[cta * 96 + 67] - host[cta * 96], host[cta * 96 + 68] - host[cta * 96]);
       fprintf(stderr, "\n   issuer, output row issued:");
       for (int k = 0; k < 10; ++k)
         if (host[cta * 96 + 48 + k]) fprintf(stderr, " %lld", host[cta * 96 + 48 + k] - host[cta * 96]);

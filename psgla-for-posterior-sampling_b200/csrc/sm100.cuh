@@ -75,6 +75,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution barrier of the cluster without the release (ptxas: MEMBAR.ALL.GPU) of cluster_sync: after mbarrier
+// initialisation published by fence.mbarrier_init.release.cluster (CUTLASS's cluster_arrive_relaxed + cluster_wait), and before
+// exit, where only "my partner no longer touches my shared / tensor memory" matters.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared::cluster address of `saddr` (a shared::cta address of this CTA's window) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   uint32_t r;
