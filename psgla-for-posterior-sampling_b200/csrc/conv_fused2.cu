@@ -112,8 +112,16 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams
     if (lane == 0) {
       tma_prefetch_desc(&tmap);
       for (int i = 0; i < F2_NSTAGE; ++i) mbar_init(&full[i], 1);
+      mbar_init(wbar, 1);
       fence_barrier_init();
       fence_proxy_async();
+      // The weights (this CTA's 32 output channels of each layer) are constant across launches: no dependency wait.  The SM's
+      // TMA queue is served in order and a bulk copy takes ~100 cycles to issue, so: the first layer's weights from here, while
+      // the previous grid drains, ahead of the input rows (the first MMA needs both); the second layer's behind the rows
+      // (warp 1, after the cluster barrier).
+      mbar_expect_tx(wbar, Cfg::W_BYTES);
+      for (int t = 0; t < 9; ++t)
+        bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES, Cfg::TAP_BYTES, wbar);
       griddep_wait();
       F2_STAMP(2);
       for (int q = 0; q < min(n_in, F2_NSTAGE); ++q) {
@@ -126,19 +134,12 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams
     tmem_alloc2(tmem_ptr_s, 512);
     tmem_relinquish2();
     if (lane == 0) {
-      // The weights (this CTA's 32 output channels of each layer) are constant across launches: no dependency wait.  The SM's
-      // TMA queue is served in order and a bulk copy takes ~100 cycles to issue, so: the first layer's weights from here,
-      // ahead of the input rows (the first MMA needs both); the second layer's behind the rows, below.
-      mbar_init(wbar, 1);
       mbar_init(wbar2, 1);
       mbar_init(wready, 1);
       mbar_init(wready2, 1);
       mbar_init(done, 1);
       fence_barrier_init();
       fence_proxy_async();
-      mbar_expect_tx(wbar, Cfg::W_BYTES);
-      for (int t = 0; t < 9; ++t)
-        bulk_load(smem_w + t * Cfg::TAP_BYTES, p.weights + (size_t)t * Cfg::TAP_BYTES_FULL + rank * Cfg::TAP_BYTES, Cfg::TAP_BYTES, wbar);
     }
     __syncwarp();
   } else {
