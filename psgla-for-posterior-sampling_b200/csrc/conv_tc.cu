@@ -469,51 +469,101 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       mbar_wait(wbar, 0);
       mbar_wait_cluster(wready, 0);
       tc_fence_after();
-      uint32_t L0 = 0, T = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
-        int waited = 0;
-        const int ylast = c.y0 + c.rcur - 1;
-        for (int y = c.y0; y <= ylast; ++y, ++T) {
-          const int need = min(y + 1, c.yhi) - c.ylo + 1;
-          while (waited < need) {
-            const uint32_t q = L0 + waited;
-            mbar_wait(&afull[q % TS_NA], (q / TS_NA) & 1);
-            ++waited;
-          }
-          const uint32_t acc = T % TS_NACC;
-          mbar_wait(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * NOUT;
-          if (elect_one()) {
-            uint32_t accumulate = 0;
+      if (p.lean_issue) {
+        // ONE thread runs the whole issue loop, barrier waits included: the tensor pipe's queue is shallow, so whatever the
+        // issuing thread executes between two MMAs beyond a few dozen cycles is a bubble in the pipe (the warp-uniform wait /
+        // elect / syncwarp boundary below costs ~160 cycles per row: conv_fused2.cu has the measurement).  A source row is
+        // awaited right before the first 12 MMAs that read it.
+        if (elect_one()) {
+          uint32_t L0 = 0, T = 0;
+#pragma unroll 1
+          for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const ItemCoord c = decode_item(p, item);
+            int waited = 0;
+            const int ylast = c.y0 + c.rcur - 1;
+#pragma unroll 1
+            for (int y = c.y0; y <= ylast; ++y, ++T) {
+              const uint32_t acc = T % TS_NACC;
+              mbar_wait_spin(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
+              const uint32_t d_tmem = tmem_base + acc * NOUT;
+              uint32_t accumulate = 0;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const int yy = y + dy - 1;
-              if (yy < 0 || yy >= p.H) continue;
-              const uint32_t q = L0 + (uint32_t)(yy - c.ylo);
-              const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
-                  umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
-                  accumulate = 1;
+              for (int dy = 0; dy < 3; ++dy) {
+                const int yy = y + dy - 1;
+                if (yy < 0 || yy >= p.H) continue;
+                const int rel = yy - c.ylo;
+                const uint32_t q = L0 + (uint32_t)rel;
+                if (rel == waited) {
+                  mbar_wait_spin(&afull[q % TS_NA], (q / TS_NA) & 1);
+                  ++waited;
                 }
+                tc_fence_after();
+                const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
+                    umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate | (uint32_t)(dx | k));
+                  }
+                }
+                accumulate = 1;
+                if ((dy == 0 && y - 1 >= c.ylo) || y == ylast) umma_commit2(&aempty[q % TS_NA], 3);
               }
-              if (dy == 0 && y - 1 >= c.ylo) umma_commit2(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA], 3);
+              umma_commit2(&tfull[acc], 3);
             }
-            umma_commit2(&tfull[acc], 3);
-            if (y == ylast)
-              for (int yy = y; yy <= c.yhi; ++yy) umma_commit2(&aempty[(L0 + (uint32_t)(yy - c.ylo)) % TS_NA], 3);
+            L0 += (uint32_t)(c.yhi - c.ylo + 1);
           }
-          __syncwarp();
+          umma_commit2(done, 3);
         }
-        L0 += (uint32_t)(c.yhi - c.ylo + 1);
+        __syncwarp();
+      } else {
+        uint32_t L0 = 0, T = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const ItemCoord c = decode_item(p, item);
+          int waited = 0;
+          const int ylast = c.y0 + c.rcur - 1;
+          for (int y = c.y0; y <= ylast; ++y, ++T) {
+            const int need = min(y + 1, c.yhi) - c.ylo + 1;
+            while (waited < need) {
+              const uint32_t q = L0 + waited;
+              mbar_wait(&afull[q % TS_NA], (q / TS_NA) & 1);
+              ++waited;
+            }
+            const uint32_t acc = T % TS_NACC;
+            mbar_wait(&tempty[acc], ((T / TS_NACC) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * NOUT;
+            if (elect_one()) {
+              uint32_t accumulate = 0;
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const int yy = y + dy - 1;
+                if (yy < 0 || yy >= p.H) continue;
+                const uint32_t q = L0 + (uint32_t)(yy - c.ylo);
+                const uint32_t a_t = tmem_base + TS_A_COL0 + (q % TS_NA) * 96u;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t bl = w_lo + (uint32_t)(((dy * 3 + dx) * Cfg::TAP_BYTES + k * 32) >> 4);
+                    umma_bf16_ts2(d_tmem, a_t + dx * 32 + k * 8, ((uint64_t)DESC_HI << 32) | bl, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+                if (dy == 0 && y - 1 >= c.ylo) umma_commit2(&aempty[(L0 + (uint32_t)(y - 1 - c.ylo)) % TS_NA], 3);
+              }
+              umma_commit2(&tfull[acc], 3);
+              if (y == ylast)
+                for (int yy = y; yy <= c.yhi; ++yy) umma_commit2(&aempty[(L0 + (uint32_t)(yy - c.ylo)) % TS_NA], 3);
+            }
+            __syncwarp();
+          }
+          L0 += (uint32_t)(c.yhi - c.ylo + 1);
+        }
+        if (elect_one()) umma_commit2(done, 3);
+        __syncwarp();
       }
-      if (elect_one()) umma_commit2(done, 3);
-      __syncwarp();
     }
     mbar_wait(done, 0);  // both CTAs: no MMA still reads this CTA's shared / tensor memory, no commit is still in flight
   } else if (warp < 6) {
@@ -773,6 +823,15 @@ static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaS
     if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: conv3x3_ts2_kernel: %d co-resident CTA pairs (occupancy query %d)\n", max_clusters, n);
   }
   plan_items_pair(&p, max_clusters);
+  {
+    // PSGLA_CONV_ISSUE=0: the warp-uniform issue loop (A/B runs); default: the single-thread one
+    static int lean = -1;
+    if (lean < 0) {
+      const char* e = getenv("PSGLA_CONV_ISSUE");
+      lean = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.lean_issue = lean;
+  }
   const int pairs = p.n_items / 2;
   cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, max_clusters)));
   if (getenv("PSGLA_VERBOSE")) fprintf(stderr, "psgla_b200: pair conv B=%d H=%d W=%d: R=%d items=%d grid=%u\n", p.B, p.H, p.W, p.R, p.n_items, cfg.gridDim.x);

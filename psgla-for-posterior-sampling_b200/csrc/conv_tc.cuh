@@ -69,6 +69,7 @@ struct ConvParams {
   int B, H, W;
   int R, strips, row_blocks, n_items;
   int reverse;  // walk the work items back to front (see decode_item)
+  int lean_issue;  // pair kernel: one thread runs the MMA issue loop incl. its barrier waits (conv_tc.cu)
   const uint8_t* weights;  // 9 taps, swizzled
   const float* bias;       // NOUT floats
   int relu;
