@@ -473,18 +473,36 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
     conv_launch_ms = conv_ms / (reps * 18)
 
     # ---- the reference's own shape of run: ONE chain (launch-latency bound: 20 launches of ~8 us per iteration)
-    run1 = P.psgla_run(init, dg, den, n_iter=200, n_chains=1, chain_id0=rank, **kw)
-    for i in range(20):
+    # Two hidden layers per launch here (csrc/conv_fused2.cu): 11 launches per iteration.  The loop is latency-bound, so it is
+    # timed in ITS OWN steady state: ~0.2 s of iterations first -- the power-capped 32-chain blocks above leave the SM clock
+    # low for tens of milliseconds (134 us per iteration right after them, 125 us once the clock is back, same box).
+    run1 = P.psgla_run(init, dg, den, n_iter=2000, n_chains=1, chain_id0=rank, **kw)
+    for i in range(1500):
         run1.step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(20, 120):
+    for i in range(1500, 1800):
         run1.step(i)
     e1.record()
     torch.cuda.synchronize()
-    single_chain_its = 100.0 / (e0.elapsed_time(e1) * 1e-3)
+    single_chain_its = 300.0 / (e0.elapsed_time(e1) * 1e-3)
     del run1
+    os.environ["PSGLA_CONV_FUSE2"] = "0"  # the same loop with one layer per launch (the switch is read per call)
+    try:
+        run1 = P.psgla_run(init, dg, den, n_iter=800, n_chains=1, chain_id0=rank, **kw)
+        for i in range(300):
+            run1.step(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(300, 600):
+            run1.step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        single_chain_unfused_its = 300.0 / (e0.elapsed_time(e1) * 1e-3)
+        del run1
+    finally:
+        os.environ.pop("PSGLA_CONV_FUSE2", None)
 
     # ---- the fused Langevin "pre" kernel alone (HBM-bound stage)
     def pre_only():
@@ -580,7 +598,9 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
         "single_chain": {"iterations_per_sec": single_chain_its, "us_per_iteration": 1e6 / single_chain_its,
                          "tensor_tflops": DNCNN_FLOP_PER_PIXEL * H * Wd * single_chain_its / 1e12,
                          "frac_of_burst_peak": DNCNN_FLOP_PER_PIXEL * H * Wd * single_chain_its / 1e12 / peaks["bf16_tflops"],
-                         "note": "the reference's own run shape (configs[2]: one chain of one 256 x 256 image), 20 launches per iteration"},
+                         "us_per_iteration_one_layer_per_launch": 1e6 / single_chain_unfused_its,
+                         "note": "the reference's own run shape (configs[2]: one chain of one 256 x 256 image): 11 launches per "
+                                 "iteration, two hidden layers per launch (conv_fused2.cu, bit-identical to the 20-launch form)"},
         "state_finite": finite, "state_absmax": x_absmax,
         "per_step_ms": [round(v, 3) for v in per_step],
     }

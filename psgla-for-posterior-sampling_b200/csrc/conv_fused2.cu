@@ -63,6 +63,15 @@ struct F2Params {
   do {                                                                       \
     if (f.trace) f.trace[(size_t)blockIdx.x * 96 + (k)] = clock64();         \
   } while (0)
+// wall-clock (ns) stamps in slots 90..: the pipelined timeline across launches (PSGLA_F2_TRACE=2, no synchronisation)
+#define F2_GSTAMP(k)                                                         \
+  do {                                                                       \
+    if (f.trace) {                                                           \
+      unsigned long long g_;                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_));                 \
+      f.trace[(size_t)blockIdx.x * 96 + (k)] = (long long)g_;                \
+    }                                                                        \
+  } while (0)
 
 // 16 bytes into the shared memory of another CTA of the cluster; the bytes count as a transaction on that CTA's mbarrier
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t mbar_cluster_addr) {
@@ -100,7 +109,10 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   griddep_launch_dependents();
-  if (threadIdx.x == 0) F2_STAMP(0);
+  if (threadIdx.x == 0) {
+    F2_STAMP(0);
+    F2_GSTAMP(90);
+  }
 
   // the pair's work item: output rows [y0, y0 + rcur), intermediate rows [m_lo, m_hi], input rows [i_lo, i_hi]
   const ItemCoord c = decode_item(p, blockIdx.x);
@@ -127,6 +139,7 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       tma_load_3d(smem_w, &tmap_w1, wbar, 0, (int)rank * 32, 0);  // one box: 9 taps x this CTA's 32 rows x 128 B, as they lie
       griddep_wait();
       F2_STAMP(2);
+      F2_GSTAMP(91);
       for (int q = 0; q < min(n_in, F2_NSTAGE); ++q) {
         mbar_expect_tx(&full[q], Cfg::BOX_BYTES);
         tma_load_4d(ring + q * Cfg::SLOT_BYTES, &tmap, &full[q], 0, c.x0 - 1, i_lo + q, c.b);
@@ -420,7 +433,10 @@ conv3x3_fused2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   }
   tc_fence_before();
   cluster_sync_relaxed();
-  if (threadIdx.x == 0) F2_STAMP(12);
+  if (threadIdx.x == 0) {
+    F2_STAMP(12);
+    F2_GSTAMP(92);
+  }
   // neither CTA may exit (or free tensor memory) while its partner can still signal, read or write it
   if (warp == 1) {
     tc_fence_after();
@@ -515,11 +531,25 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   p.n_items = B * 2 * p.row_blocks;
   F2Params f{w2, b2, (__nv_bfloat16*)out, nullptr};
   static long long* trace_dev = nullptr;
-  const bool trace = getenv("PSGLA_F2_TRACE") != nullptr;
+  const char* trace_env = getenv("PSGLA_F2_TRACE");
+  const bool trace = trace_env != nullptr && trace_env[0] == '1';
   if (trace) {
     if (!trace_dev) PSGLA_CUDA_TRY(cudaMalloc(&trace_dev, 512 * 96 * sizeof(long long)));
     PSGLA_CUDA_TRY(cudaMemsetAsync(trace_dev, 0, 512 * 96 * sizeof(long long), st));
     if (p.n_items <= 512) f.trace = trace_dev;
+  }
+  // PSGLA_F2_TRACE=2: the next 36 launches write their stamps side by side, nothing synchronises in between; after the last
+  // one the wall-clock timeline (entry / previous grid complete / exit of the earliest and latest CTA of each launch) is printed
+  constexpr int kPipeLaunches = 36;
+  static long long* pipe_dev = nullptr;
+  static int pipe_n = 0;
+  const bool pipe = trace_env != nullptr && trace_env[0] == '2' && p.n_items <= 160 && pipe_n < kPipeLaunches;
+  if (pipe) {
+    if (!pipe_dev) {
+      PSGLA_CUDA_TRY(cudaMalloc(&pipe_dev, (size_t)kPipeLaunches * 160 * 96 * sizeof(long long)));
+      PSGLA_CUDA_TRY(cudaMemset(pipe_dev, 0, (size_t)kPipeLaunches * 160 * 96 * sizeof(long long)));
+    }
+    f.trace = pipe_dev + (size_t)pipe_n * 160 * 96;
   }
   CUtensorMap map, map_w1, map_w2;
   rc = get_act_tensor_map(&map, in, B, H, W, 64, BOX_W);
@@ -544,7 +574,38 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   cfg.numAttrs = 2;
   PSGLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused2_kernel, map, map_w1, map_w2, p, f));
   *applicable = 1;
-  if (f.trace) {
+  if (pipe && ++pipe_n == kPipeLaunches) {
+    std::vector<long long> host((size_t)kPipeLaunches * 160 * 96);
+    PSGLA_CUDA_TRY(cudaStreamSynchronize(st));
+    PSGLA_CUDA_TRY(cudaMemcpy(host.data(), pipe_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long prev_exit = 0;
+    for (int l = 0; l < kPipeLaunches; ++l) {
+      const long long* h = host.data() + (size_t)l * 160 * 96;
+      long long e_min = 0, e_max = 0, w_min = 0, w_max = 0, x_min = 0, x_max = 0, cyc_max = 0;
+      int slow = 0;
+      for (int cta = 0; cta < p.n_items; ++cta) {
+        const long long e = h[cta * 96 + 90], w = h[cta * 96 + 91], x = h[cta * 96 + 92];
+        if (!e) continue;
+        if (!e_min || e < e_min) e_min = e;
+        if (e > e_max) e_max = e;
+        if (!w_min || w < w_min) w_min = w;
+        if (w > w_max) w_max = w;
+        if (!x_min || x < x_min) x_min = x;
+        if (x > x_max) x_max = x, slow = cta;
+        cyc_max = std::max(cyc_max, h[cta * 96 + 12] - h[cta * 96]);
+      }
+      const long long* hs = h + slow * 96;
+      fprintf(stderr,
+              "f2 pipe launch %2d: period %6lld ns | after the previous launch's last exit: first entry %6lld last entry %6lld, "
+              "grid wait done %6lld .. %6lld, first exit %6lld, last exit (cta %3d) %6lld | that CTA: entry %6lld wait %6lld, cycles "
+              "entry->wait %lld ->rows %lld ->exit %lld\n",
+              l, prev_exit ? x_max - prev_exit : 0, e_min - prev_exit, e_max - prev_exit, w_min - prev_exit, w_max - prev_exit,
+              x_min - prev_exit, slow, x_max - prev_exit, hs[90] - prev_exit, hs[91] - prev_exit, hs[2] - hs[0], hs[4] - hs[0],
+              hs[12] - hs[0]);
+      prev_exit = x_max;
+    }
+  }
+  if (trace && f.trace) {
     // clock64 stamps (cycles after the CTA's entry): 1 prologue + cluster sync done, 2 previous grid complete, 3 weights of both
     // CTAs landed, 4 first input row landed, 5 / 8 first MMA of phase 1 / 2 may issue, 6 / 7 first / last intermediate row's
     // accumulator complete, 9 all MMAs complete, 10 / 11 epilogue groups done (stores complete), 12 final cluster sync
