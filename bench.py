@@ -467,10 +467,10 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
 
     hidden_layers()
     reps = 5
-    for _ in range(reps):
+    for _ in range(9):
         timer.step(hidden_layers)
-    conv_ms, _ = timer.total_ms()
-    conv_launch_ms = conv_ms / (reps * 18)
+    _, conv_reps = timer.total_ms()
+    conv_launch_ms = sorted(conv_reps)[len(conv_reps) // 2] / 18  # median repetition: the block sits at the power cap
 
     # ---- the reference's own shape of run: ONE chain (launch-latency bound: 20 launches of ~8 us per iteration)
     # Two hidden layers per launch here (csrc/conv_fused2.cu): 11 launches per iteration.  The loop is latency-bound, so it is
