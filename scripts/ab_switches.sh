@@ -8,6 +8,8 @@ run() {  # run VAR=value "k expression" files...
 }
 run PSGLA_CONV_PAIR=0 "conv_layer or dncnn_forward or psgla_replay or fused_next" tests/test_image_gpu.py
 run PSGLA_CONV_SS=1 "conv_layer or dncnn_forward or psgla_replay" tests/test_image_gpu.py
+run PSGLA_CONV_FUSE2=0 "dncnn_forward or psgla_replay or reference_fixture or fused_layer" tests/test_image_gpu.py
+run PSGLA_CONV_ISSUE=0 "conv_layer or dncnn_forward or psgla_replay" tests/test_image_gpu.py
 run PSGLA_CHAIN=1 "dncnn_forward or psgla_replay or reference_fixture" tests/test_image_gpu.py
 run PSGLA_FUSE_PRE=0 "psgla_replay or batched or statistics_only or image_set" tests/test_image_gpu.py
 run PSGLA_CONV_ALTERNATE=0 "dncnn_forward or psgla_replay" tests/test_image_gpu.py
