@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -530,8 +531,13 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
   p.row_blocks = (H + R - 1) / R;
   p.n_items = B * 2 * p.row_blocks;
   F2Params f{w2, b2, (__nv_bfloat16*)out, nullptr};
+  // Development traces (PSGLA_F2_TRACE): their buffers are process-wide, so a traced launch holds this lock from here to its
+  // return; untraced launches (the product's) never take it.
+  static std::mutex trace_mutex;
   static long long* trace_dev = nullptr;
   const char* trace_env = getenv("PSGLA_F2_TRACE");
+  std::unique_lock<std::mutex> trace_lock;
+  if (trace_env != nullptr) trace_lock = std::unique_lock<std::mutex>(trace_mutex);
   const bool trace = trace_env != nullptr && trace_env[0] == '1';
   if (trace) {
     if (!trace_dev) PSGLA_CUDA_TRY(cudaMalloc(&trace_dev, 512 * 96 * sizeof(long long)));
@@ -609,9 +615,9 @@ int conv64_hidden_fused2(const void* in, void* out, const uint8_t* w1, const flo
     // clock64 stamps (cycles after the CTA's entry): 1 prologue + cluster sync done, 2 previous grid complete, 3 weights of both
     // CTAs landed, 4 first input row landed, 5 / 8 first MMA of phase 1 / 2 may issue, 6 / 7 first / last intermediate row's
     // accumulator complete, 9 all MMAs complete, 10 / 11 epilogue groups done (stores complete), 12 final cluster sync
-    static long long host[512 * 96];
+    std::vector<long long> host(512 * 96);
     PSGLA_CUDA_TRY(cudaStreamSynchronize(st));
-    PSGLA_CUDA_TRY(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    PSGLA_CUDA_TRY(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     const int ctas[] = {0, 1, p.n_items / 2, p.n_items - 2};
     for (int cta : ctas) {
       fprintf(stderr, "f2 trace cta %3d:", cta);
