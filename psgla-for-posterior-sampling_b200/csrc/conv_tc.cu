@@ -375,9 +375,10 @@ struct ConvTs2Cfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
-// RES: the layer has a residual input and fetches it by TMA (epilogue_hidden_tmares); a separate instantiation so that the
-// plain layers (all of DnCNN) keep their own register allocation and code (sharing one kernel cost them 5 %, ncu).
-template <int NOUT, bool RES>
+// RES: the layer has a residual input and fetches it by TMA (epilogue_hidden_tmares), RES = 2: and a second one (the U-Net
+// skip tensor, per-thread loads); separate instantiations so that the plain layers (all of DnCNN) keep their own register
+// allocation and code (sharing one kernel cost them 5 %, ncu), and the single-residual layers theirs.
+template <int NOUT, int RES>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
@@ -603,7 +604,7 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int ew = warp - 6;
     uint32_t T = 0;
     if (RES)
-      epilogue_hidden_tmares<NOUT, TS_NACC>(p, &tmap_out, &tmap_res, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES,
+      epilogue_hidden_tmares<NOUT, TS_NACC, RES == 2>(p, &tmap_out, &tmap_res, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES,
                                             rbar + 2 * ew, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, tempty_c);
     else
       epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
@@ -783,7 +784,7 @@ static void plan_items_pair(ConvParams* p, int n_clusters) {
   p->n_items = p->B * p->strips * p->row_blocks;
 }
 
-template <int NOUT, bool RES>
+template <int NOUT, int RES>
 static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaStream_t st) {
   using Cfg = ConvTs2Cfg<NOUT>;
   CUtensorMap map, map_out;
@@ -841,7 +842,8 @@ static int launch_conv_ts2_t(const void* in, void* out_bf16, ConvParams p, cudaS
 
 template <int NOUT>
 static int launch_conv_ts2(const void* in, void* out_bf16, const ConvParams& p, cudaStream_t st) {
-  return p.res1 ? launch_conv_ts2_t<NOUT, true>(in, out_bf16, p, st) : launch_conv_ts2_t<NOUT, false>(in, out_bf16, p, st);
+  if (!p.res1) return launch_conv_ts2_t<NOUT, 0>(in, out_bf16, p, st);
+  return p.res2 ? launch_conv_ts2_t<NOUT, 2>(in, out_bf16, p, st) : launch_conv_ts2_t<NOUT, 1>(in, out_bf16, p, st);
 }
 
 // PSGLA_CONV_PAIR=0 falls back to the single-CTA TS kernel (A/B runs)

@@ -228,7 +228,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
 // ahead; the lanes then read-modify-write the box in shared memory and the TMA store ships it.  Box ownership: the load for
 // row n + 1 into box b' is issued after cp.async.bulk.wait_group.read 1, i.e. once the store of row n - 1 has finished
 // reading b'; generic writes precede the store by fence.proxy.async as before.
-template <int NOUT, int NACC_>
+template <int NOUT, int NACC_, bool RES2>
 __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, const CUtensorMap* tmap_out,
                                                        const CUtensorMap* tmap_res, uint8_t* stage, uint64_t* rbar,
                                                        const float* bias_s, uint64_t* tfull, uint64_t* tempty,
@@ -294,13 +294,31 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
     const int xw = c.x0 + q4 * 32;
     const bool row_has = xw < p.W;
     const uint32_t acc = T % NACC_;
-    // second residual tensor (U-Net skip, one layer per scale): per-thread loads, issued before the accumulator is awaited
-    const bool has_res2 = p.res2 != nullptr && xw + lane < p.W;
+    // second residual tensor (U-Net skip, one layer per scale, its own instantiation): per-thread loads, issued before the
+    // accumulator is awaited
+    const bool has_res2 = RES2 && xw + lane < p.W;
     const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
-    uint4 rr2[NOUT / 8];
-    if (has_res2) {  // 32 bytes per lane and access: full sectors (16-byte accesses cost this layer 1 266 instead of ~1 000 us)
+    uint4 rr2[RES2 ? NOUT / 8 : 1];
+    if (RES2 && has_res2) {  // 32 bytes per lane and access: full sectors (16-byte accesses cost this layer 1 266 instead of ~1 000 us)
 #pragma unroll
-      for (int j = 0; j < NOUT / 8; j += 2) ldg256(p.res2 + roff + 8 * j, rr2[j], rr2[j + 1]);
+      for (int j = 0; j < NOUT / 8; j += 2) ldg256(p.res2 + roff + 8 * j, rr2[RES2 ? j : 0], rr2[RES2 ? j + 1 : 0]);
+    }
+    // This row's residual box landed a row ago: all of it goes into registers in one batch, ahead of the wait for the
+    // accumulator.  (Chunk by chunk inside the loop below -- load, add, pack, store to the same address -- every chunk paid a
+    // shared-memory round trip behind the previous chunk's store, and the epilogue warps, not HBM or the tensor pipe, bound
+    // the layer: 885 -> 738 us at 64 chains of 320 x 480, profiles/r02_drunet_conv64_full.txt.  With the second residual's 32
+    // registers live as well the batch is two halves inside the loop: all three vectors at once spill, 1 750 us.)
+    uint8_t* stage_cur = stage + box * BOX;
+    const uint32_t stage_row = smem_u32(stage_cur) + lane * (NOUT * 2);
+    constexpr int RB = RES2 ? NOUT / 16 : NOUT / 8;  // chunks per batch
+    uint4 rr[RB];
+    if (row_has) {
+      mbar_wait(&rbar[box], cnt[box] & 1u);  // (pixels beyond W: zero fill)
+      ++cnt[box];
+      if (!RES2) {
+#pragma unroll
+        for (int j = 0; j < NOUT / 8; ++j) rr[j] = ld_shared_v4_nc(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4));  // 128B swizzle
+      }
     }
     mbar_wait(&tfull[acc], (T / NACC_) & 1);
     tc_fence_after();
@@ -316,12 +334,6 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
       else
         mbar_arrive(&tempty[acc]);
     }
-    if (row_has) {
-      mbar_wait(&rbar[box], cnt[box] & 1u);  // this row's residual box has landed (pixels beyond W: zero fill)
-      ++cnt[box];
-    }
-    uint8_t* stage_cur = stage + box * BOX;
-    const uint32_t stage_row = smem_u32(stage_cur) + lane * (NOUT * 2);
 #pragma unroll
     for (int j = 0; j < NOUT / 8; ++j) {
       const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
@@ -329,15 +341,18 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
                     __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                     __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
                     __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
-      const uint32_t saddr = stage_row + ((uint32_t)(j ^ (lane & 7)) << 4);  // 128B swizzle: chunk ^= row & 7
-      if (row_has) add_bf16x8(f, ld_shared_v4(saddr));
-      if (has_res2) add_bf16x8(f, rr2[j]);
+      if (RES2 && row_has && j % RB == 0) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) rr[i] = ld_shared_v4_nc(stage_row + ((uint32_t)((j + i) ^ (lane & 7)) << 4));
+      }
+      if (row_has) add_bf16x8(f, rr[j % RB]);
+      if (RES2 && has_res2) add_bf16x8(f, rr2[RES2 ? j : 0]);
       uint4 o;
       o.x = pack_bf16x2(f[0], f[1], relu);
       o.y = pack_bf16x2(f[2], f[3], relu);
       o.z = pack_bf16x2(f[4], f[5], relu);
       o.w = pack_bf16x2(f[6], f[7], relu);
-      st_shared_v4(saddr, o);
+      st_shared_v4_nc(stage_row + ((uint32_t)(j ^ (lane & 7)) << 4), o);
     }
     fence_proxy_async();
     __syncwarp();
