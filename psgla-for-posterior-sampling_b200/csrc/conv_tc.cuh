@@ -35,6 +35,28 @@ __device__ __forceinline__ void add_bf16x8(float (&f)[8], const uint4 r) {
   }
 }
 
+// The 8 biases of 16-byte output chunk j.  The epilogues fetch them ONE CHUNK AHEAD with explicit shared-space loads: through a
+// generic pointer they compile to LD.E, and placed after the previous chunk's staging store (a "memory"-clobbering asm
+// statement keeps program order) every chunk paid a long-scoreboard round trip -- the first layer, whose epilogue is its
+// critical path, ran at 1 240 cycles per row (profiles/r02_first_last_layer_full.txt).  SMEM = false: bias in global memory
+// (the layer-chain experiment).
+struct BiasPair {
+  float4 b0, b1;
+};
+template <bool SMEM>
+__device__ __forceinline__ BiasPair load_bias_pair(const float* bias, uint32_t bias_saddr, int j) {
+  BiasPair r;
+  if (SMEM) {
+    r.b0 = ld_shared_f4_nc(bias_saddr + 32u * (uint32_t)j);
+    r.b1 = ld_shared_f4_nc(bias_saddr + 32u * (uint32_t)j + 16u);
+  } else {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+    r.b0 = b4[2 * j];
+    r.b1 = b4[2 * j + 1];
+  }
+  return r;
+}
+
 template <int CIN, int NOUT, int EPI>
 struct ConvCfg {
   static constexpr int ROW_BYTES = CIN * 2;
@@ -135,7 +157,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, bool relu) {
 
 // Hidden layers: TMEM -> +bias -> ReLU -> bf16 -> 128B-swizzled staging box in shared memory -> one TMA store of
 // 32 pixels x NOUT channels per warp and row (clipped at the image edge by the tensor map).
-template <int NOUT, int NACC_>
+template <int NOUT, int NACC_, bool BIAS_SMEM = true>
 __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUtensorMap* tmap_out, uint8_t* stage,
                                                 const float* bias_s, uint64_t* tfull, uint64_t* tempty,
                                                 uint32_t tmem_base, int grp, int q4, int lane, uint32_t& T,
@@ -146,7 +168,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
   // stage_bufs == 2: the warp alternates between two staging boxes, so a row is staged while the previous row's TMA
   // store is still reading its box (the store's read latency otherwise serialises with the warp's work on every row)
   uint32_t nrow = 0;
-  const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+  const uint32_t bias_sa = BIAS_SMEM ? smem_u32(bias_s) : 0u;
   const bool relu = p.relu != 0;
   if (lane == 0) tma_prefetch_desc(tmap_out);
   // the residual tensors come from earlier kernels and are now read ahead of the accumulator (i.e. before anything in this
@@ -189,9 +211,11 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
           mbar_arrive(&tempty[acc]);
       }
       __syncwarp();
+      BiasPair bp = load_bias_pair<BIAS_SMEM>(bias_s, bias_sa, 0);
 #pragma unroll
       for (int j = 0; j < NOUT / 8; ++j) {  // 16-byte chunk j = channels 8j..8j+7
-        const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+        const float4 b0 = bp.b0, b1 = bp.b1;
+        if (j + 1 < NOUT / 8) bp = load_bias_pair<BIAS_SMEM>(bias_s, bias_sa, j + 1);
         float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
                       __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                       __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
@@ -264,7 +288,7 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
       tma_load_4d(stage + box * BOX, tmap_res, &rbar[box], 0, xw, r.y, r.c.b);
     }
   };
-  const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+  const uint32_t bias_sa = smem_u32(bias_s);
   const bool relu = p.relu != 0;
   if (lane == 0) {
     tma_prefetch_desc(tmap_out);
@@ -334,9 +358,11 @@ __device__ __forceinline__ void epilogue_hidden_tmares(const ConvParams& p, cons
       else
         mbar_arrive(&tempty[acc]);
     }
+    BiasPair bp = load_bias_pair<true>(bias_s, bias_sa, 0);
 #pragma unroll
     for (int j = 0; j < NOUT / 8; ++j) {
-      const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+      const float4 b0 = bp.b0, b1 = bp.b1;
+      if (j + 1 < NOUT / 8) bp = load_bias_pair<true>(bias_s, bias_sa, j + 1);
       float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
                     __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                     __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,

@@ -216,7 +216,7 @@ conv3x3_ts_chain_kernel(const __grid_constant__ CUtensorMap map_ld0, const __gri
     uint32_t T = 0;
     for (int l = 0; l < cp.n_layers; ++l) {
       const float* bias = reinterpret_cast<const float*>(cp.weights0 + (size_t)l * HIDDEN_LAYER_STRIDE + Cfg::W_BYTES);
-      epilogue_hidden<NOUT, TS_NACC>(p, ((l + 1) & 1) ? &map_st1 : &map_st0, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias,
+      epilogue_hidden<NOUT, TS_NACC, false>(p, ((l + 1) & 1) ? &map_st1 : &map_st0, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias,
                                      tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, T, 0, Cfg::STAGE_BUFS);
       // other CTAs of this grid read these rows after the barrier: wait for the stores' WRITES, not only their reads
       if (lane == 0) bulk_wait_group0();

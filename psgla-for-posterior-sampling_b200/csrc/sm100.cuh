@@ -362,6 +362,11 @@ __device__ __forceinline__ uint4 ld_shared_v4_nc(uint32_t saddr) {
 __device__ __forceinline__ void st_shared_v4_nc(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+__device__ __forceinline__ float4 ld_shared_f4_nc(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 // One 128-byte K-major row (64 bf16) of a 128B-swizzled tile whose base is 1024-byte aligned -> 32 registers in
 // logical order: 16-byte chunk j of row r sits at physical chunk j ^ (r & 7).
 __device__ __forceinline__ void ld_swizzled_row128(uint32_t tile_saddr, int row, uint32_t (&v)[32]) {
