@@ -607,8 +607,8 @@ conv3x3_ts2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       epilogue_hidden_tmares<NOUT, TS_NACC, RES == 2>(p, &tmap_out, &tmap_res, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES,
                                             rbar + 2 * ew, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane, tempty_c);
     else
-      epilogue_hidden<NOUT, TS_NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                     tmem_base, ew >> 2, warp & 3, lane, T, tempty_c, Cfg::STAGE_BUFS);
+      epilogue_hidden<NOUT, TS_NACC, true, false>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
+                                                  tmem_base, ew >> 2, warp & 3, lane, T, tempty_c, Cfg::STAGE_BUFS);
   }
   tc_fence_before();
   cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still signal or read it

@@ -157,7 +157,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, bool relu) {
 
 // Hidden layers: TMEM -> +bias -> ReLU -> bf16 -> 128B-swizzled staging box in shared memory -> one TMA store of
 // 32 pixels x NOUT channels per warp and row (clipped at the image edge by the tensor map).
-template <int NOUT, int NACC_, bool BIAS_SMEM = true>
+// ALLOW_RES = false: the caller never has residual inputs (the pair kernel's plain instantiation, i.e. every hidden layer of
+// DnCNN): the per-thread residual path, a divergent branch per chunk inside the unrolled loop, is compiled out.
+template <int NOUT, int NACC_, bool BIAS_SMEM = true, bool ALLOW_RES = true>
 __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUtensorMap* tmap_out, uint8_t* stage,
                                                 const float* bias_s, uint64_t* tfull, uint64_t* tempty,
                                                 uint32_t tmem_base, int grp, int q4, int lane, uint32_t& T,
@@ -173,7 +175,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
   if (lane == 0) tma_prefetch_desc(tmap_out);
   // the residual tensors come from earlier kernels and are now read ahead of the accumulator (i.e. before anything in this
   // warp depends on the producer's own griddepcontrol.wait)
-  if (p.res1 != nullptr) griddep_wait();
+  if (ALLOW_RES && p.res1 != nullptr) griddep_wait();
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     const ItemCoord c = decode_item(p, item);
     const int xw = c.x0 + q4 * 32;  // first pixel of this warp's 32-pixel box
@@ -181,7 +183,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
       if ((int)(T & 1) != grp) continue;
       const uint32_t acc = T % NACC_;
       // residual inputs (DRUNet) are fetched while the row's MMAs are still in flight
-      const bool has_res = p.res1 != nullptr && xw + lane < p.W;
+      const bool has_res = ALLOW_RES && p.res1 != nullptr && xw + lane < p.W;
       const size_t roff = (((size_t)c.b * p.H + y) * p.W + (xw + lane)) * NOUT;
       uint4 rr[NOUT / 8];
       if (has_res) {
@@ -220,7 +222,7 @@ __device__ __forceinline__ void epilogue_hidden(const ConvParams& p, const CUten
                       __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                       __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
                       __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
-        if (has_res) {
+        if (ALLOW_RES && has_res) {
           add_bf16x8(f, rr[j]);
           if (p.res2) add_bf16x8(f, *reinterpret_cast<const uint4*>(p.res2 + roff + 8 * j));
         }
