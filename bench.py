@@ -577,12 +577,14 @@ def bench_image(args, P, torch, rank, ws, dev, peaks):
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)", "launch_ms": conv_launch_ms,
-                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r01j_conv3x3_ts2_full.txt): 273.7 MB read +
-                     # 218.4 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2.
-                     # Same capture: tensor pipe active 75.2 % of the active cycles (single-CTA TS kernel: 62.4 %).
-                     "traffic": 492.2e6 if (B == 32 and H == 256) else None,
-                     "traffic_source": "profiles/r01j_conv3x3_ts2_full.txt",
-                     "ncu_tensor_pipe_active_pct": 75.2},
+                     # ncu --set full, one launch at 32 chains of 256 x 256 (profiles/r02_conv3x3_ts2_full.txt): 274.8 MB read +
+                     # 218.6 MB written against 536.9 MB algorithmic (bf16 in + out); part of the output is still in L2.
+                     # Same capture: 101.2 us for the launch alone (1 527 TFLOP/s), tensor pipe active 88.1 % of the active and
+                     # 80.8 % of the elapsed cycles (round 1: 75.2 %; single-CTA TS kernel: 62.4 %).  Timed here back to back at the
+                     # power cap, the kernel sits at what cuBLAS sustains there.
+                     "traffic": 493.3e6 if (B == 32 and H == 256) else None,
+                     "traffic_source": "profiles/r02_conv3x3_ts2_full.txt",
+                     "ncu_tensor_pipe_active_pct": 88.1, "ncu_launch_us_alone": 101.2},
         "whole_iteration_tensor_tflops": step_tflops,
         "whole_iteration_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "pre_kernel": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -161,8 +161,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int ew = warp - 2;
     uint32_t T = 0;
     if (EPI == EPI_HIDDEN)
-      epilogue_hidden<NOUT, NACC>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull, tempty,
-                                  tmem_base, ew >> 2, warp & 3, lane, T, 0, Cfg::STAGE_BUFS);
+      epilogue_hidden<NOUT, NACC, true, CIN != 16>(p, &tmap_out, smem + Cfg::OFF_STAGE + ew * Cfg::STAGE_BYTES, bias_s, tfull,
+                                                   tempty, tmem_base, ew >> 2, warp & 3, lane, T, 0,
+                                                   Cfg::STAGE_BUFS);  // the 3-channel first layers have no residual input
     else
       epilogue_post<NOUT, NACC>(p, bias_s, tfull, tempty, tmem_base, ew >> 2, warp & 3, lane);
   }
