@@ -114,3 +114,36 @@ def test_next_pre_argument_errors_without_gpu(built):
     rc = lib.psgla_dncnn_residual_post_next(20, fake, shape, fake, fake, 1 << 30, fake, ctypes.byref(post), fake, None, None, None,
                                             ctypes.byref(bad_b), None)
     assert rc == -1 and b"mask_B" in lib.psgla_last_error()
+
+
+def _sass(obj):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    return subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
+
+
+def test_sass_is_blackwell_native(built):
+    """What the build produced, read back from the objects (no GPU needed): the conv kernels issue tcgen05 MMAs (UTCHMMA, the
+    CTA-pair ones .2CTA), move tiles by TMA (UTMALDG / UTMASTG) and read accumulators from tensor memory (LDTM); nothing falls
+    back to the legacy warp-level mma.sync (HMMA); and the weight-resident conv kernels read their bias vector with shared-space
+    loads -- as generic LD.E loads behind every chunk's staging store they cost the hidden layers 13 %."""
+    build_dir = os.path.join(os.path.dirname(built._lib.LIB_PATH), "build")
+    conv_tc = _sass(os.path.join(build_dir, "conv_tc.o"))
+    conv_gemm = _sass(os.path.join(build_dir, "conv_gemm.o"))
+    fused2 = _sass(os.path.join(build_dir, "conv_fused2.o"))
+    for name, text in (("conv_tc", conv_tc), ("conv_gemm", conv_gemm), ("conv_fused2", fused2)):
+        assert text.count("UTCHMMA") > 0, name
+        assert text.count("UTCHMMA.2CTA") > 0, name
+        assert text.count("UTMALDG") > 0, name
+        assert text.count("LDTM") > 0, name
+        assert len(re.findall(r"\bHMMA\b", text)) == 0, name
+    assert conv_tc.count("UTMASTG") > 0 and conv_tc.count("STTM") > 0
+    # per kernel of conv_tc.o: generic 128-bit loads (the old bias path) only where a residual / bias pointer may be global
+    for fn, body in re.findall(r"Function : (\S+)\n(.*?)(?=\n\s*Function : |\Z)", conv_tc, flags=re.S):
+        if "conv3x3_ts2_kernelILi64ELi0E" in fn or "conv3x3_ts2_kernelILi64ELi1E" in fn:
+            assert body.count("LD.E.128") == 0, fn
+    gmm = _sass(os.path.join(build_dir, "gmm2d.o"))
+    assert gmm.count("FFMA2") > 0 and gmm.count("MUFU") > 0
