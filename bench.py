@@ -764,10 +764,12 @@ def gpu_reference_image(args, torch, dev):
         with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")), torch.no_grad():
             fn(init, prob["data_grad"], net, n_iter=10, **kw)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fn(init, prob["data_grad"], net, n_iter=n_iter, **kw)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+            dt = float("inf")
+            for _ in range(3):  # its eager loop is bound by the host's launch rate: best of three calls
+                t0 = time.perf_counter()
+                fn(init, prob["data_grad"], net, n_iter=n_iter, **kw)
+                torch.cuda.synchronize()
+                dt = min(dt, time.perf_counter() - t0)
         out["B%d" % B] = {"value": B * n_iter / dt, "unit": "image-iterations/s", "ms_per_iteration": dt / n_iter * 1e3,
                           "iterations": n_iter}
     return out
