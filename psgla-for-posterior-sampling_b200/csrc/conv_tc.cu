@@ -13,8 +13,10 @@
 //                                  the MMAs take A from there (N/2 instead of 32 + N/4 cycles per MMA at N = 64).  Last layer
 //                                  (NOUT = 16, fused Langevin post / next pre epilogue); single-CTA form of the hidden layers.
 //   conv3x3_ts2_kernel<NOUT,RES>   the hidden layers: a CTA PAIR (cta_group::2, M = 256) on two adjacent strips, weights split
-//                                  32 / 32 output channels between the two shared memories; RES = residual input by TMA.
-//   conv3x3_ts_chain_kernel        experiment: 18 layers in one persistent launch with a grid barrier (off by default).
+//                                  32 / 32 output channels between the two shared memories; RES = 0 plain (no residual code in
+//                                  the epilogue at all), 1 = residual input by TMA, 2 = and a second one (U-Net skip tensor).
+//   (conv_fused2.cu: two hidden layers per launch when the work is a single wave of pairs; experiments.cu: the 18-layer
+//   persistent chain kernel with a grid barrier, off by default.)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), [warps 2..5 = loaders (TS forms)], 8 epilogue warps
 // in two groups (TMEM -> bias / residual / ReLU -> bf16 -> swizzled staging box -> TMA store; or the fused Langevin step,
 // restoration_algorithms.py:238-262, for the last layer).  Consecutive layers walk their items in opposite directions
